@@ -1,0 +1,195 @@
+/*
+ * stmask_b200.h — C ABI of libstmask_b200.so
+ *
+ * B200-native (sm_100a) implementation of STMask's feature-calibration and
+ * temporal-fusion hot path.  Every entry point below replaces one third-party
+ * native operator that the reference imports (the reference ships no native
+ * code of its own; citations are into the reference tree):
+ *
+ *   stm_deform_conv2d_fwd   <- dcn_v2.DCN / dcn_v2_conv        (backbone.py:5,21-26,45)
+ *                           <- mmcv.ops.DeformConv2d           (layers/modules/Featurealign.py:3,27-31,72)
+ *                           <- mmcv.ops.ModulatedDeformConv2d  (named by the north star; same math as dcn_v2)
+ *   stm_fcb_ali_offsets     <- the closed-form box->offset map (layers/modules/Featurealign.py:46-69)
+ *   stm_correlation_fwd     <- spatial_correlation_sampler.spatial_correlation_sample
+ *                              + the /C, leaky-ReLU, concat, ReLU that follow it
+ *                              (layers/modules/track_to_segment_head.py:53-62,
+ *                               layers/functions/TF_utils.py:28-31, STMask.py:291-297)
+ *
+ * Conventions
+ *   - extern "C", plain-old-data only; no torch / C++ types cross this boundary.
+ *   - All pointers are DEVICE pointers owned by the caller (activations, packed
+ *     weights, workspace).  The library never allocates device memory, never
+ *     synchronises and keeps no pointer after return; every kernel is enqueued
+ *     on `stream` (a cudaStream_t passed as void*), so the calls are CUDA-graph
+ *     capturable.
+ *   - Activations are NHWC ("channels-last"): channel stride is 1, the other
+ *     strides are given in ELEMENTS.  Offsets / masks / correlation outputs carry
+ *     four explicit strides so both NCHW and NHWC buffers work without a copy.
+ *   - Return value: 0 (STM_OK) or a negative StmStatus; stm_last_error() returns
+ *     a thread-local message for the last failing call of the calling thread.
+ *   - There is no CPU implementation behind this ABI.
+ */
+#ifndef STMASK_B200_H_
+#define STMASK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STM_ABI_VERSION 1
+
+typedef enum StmStatus {
+  STM_OK = 0,
+  STM_ERR_INVALID_ARGUMENT = -1,   /* bad shape / stride / null pointer           */
+  STM_ERR_UNSUPPORTED = -2,        /* valid request, no kernel for it             */
+  STM_ERR_WORKSPACE = -3,          /* workspace too small                         */
+  STM_ERR_CUDA = -4,               /* a CUDA runtime / driver call failed         */
+  STM_ERR_NO_DEVICE = -5           /* no sm_100 device                            */
+} StmStatus;
+
+typedef enum StmDType {
+  STM_F32 = 0,
+  STM_BF16 = 1
+} StmDType;
+
+/* which kernel family to use; AUTO picks tcgen05 when the shape allows it */
+typedef enum StmBackend {
+  STM_BACKEND_AUTO = 0,
+  STM_BACKEND_SIMT = 1,    /* CUDA-core kernels: any shape, fp32 or bf16 storage, fp32 math */
+  STM_BACKEND_TCGEN05 = 2  /* tcgen05/TMEM/TMA kernels: bf16 storage, fp32 accumulate        */
+} StmBackend;
+
+/* ------------------------------------------------------------------------- */
+/* Deformable convolution (DCNv1 when mask == NULL, DCNv2 otherwise)          */
+/* ------------------------------------------------------------------------- */
+
+enum {
+  STM_DCN_RELU = 1,          /* y = max(y, 0) in the epilogue (Featurealign.py:72)                  */
+  STM_DCN_MASK_SIGMOID = 2,  /* mask holds logits; apply sigmoid while sampling (dcn_v2.DCN.forward) */
+  STM_DCN_ZERO_OFFSET = 4    /* offset == NULL: plain convolution through the same pipeline          */
+};
+
+/* Parameters shared by every problem of one call (one weight tensor). */
+typedef struct StmDcnConv {
+  int32_t in_c, out_c;             /* Cin, Cout (totals, not per group)                */
+  int32_t kernel_h, kernel_w;
+  int32_t stride_h, stride_w;
+  int32_t pad_h, pad_w;
+  int32_t dil_h, dil_w;
+  int32_t groups;                  /* weight groups                                    */
+  int32_t deform_groups;           /* offset groups; in_c % deform_groups == 0         */
+  int32_t dtype;                   /* StmDType of x, packed weight, bias(always f32), y */
+  int32_t offset_dtype;            /* StmDType of offset and mask                      */
+  int32_t flags;                   /* STM_DCN_*                                        */
+  int32_t backend;                 /* StmBackend                                       */
+} StmDcnConv;
+
+/* One feature map to convolve.  Several problems (e.g. the five FPN levels that
+ * share the prediction-head weights, STMask.py:91-92) go into ONE launch. */
+typedef struct StmDcnProblem {
+  int32_t batch, in_h, in_w;
+  int32_t out_h, out_w;            /* must equal floor((in + 2p - d(k-1) - 1)/s) + 1   */
+  const void* x;                   /* [batch, in_h, in_w, in_c]  NHWC                   */
+  int64_t x_stride_n, x_stride_h, x_stride_w;
+  const void* offset;              /* logical [batch, dg*2*kh*kw, out_h, out_w]; ch 2k = dy, 2k+1 = dx */
+  int64_t off_stride_n, off_stride_c, off_stride_h, off_stride_w;
+  const void* mask;                /* logical [batch, dg*kh*kw, out_h, out_w] or NULL   */
+  int64_t mask_stride_n, mask_stride_c, mask_stride_h, mask_stride_w;
+  void* y;                         /* [batch, out_h, out_w, out_c]  NHWC                */
+  int64_t y_stride_n, y_stride_h, y_stride_w;
+} StmDcnProblem;
+
+#define STM_DCN_MAX_PROBLEMS 8
+
+/* Packed weight: [out_c][kernel_h][kernel_w][in_c/groups] ("OHWI"), conv->dtype.
+ * Returns the number of BYTES the packed tensor needs. */
+size_t stm_dcn_packed_weight_bytes(const StmDcnConv* conv);
+
+/* w_oihw: contiguous [out_c, in_c/groups, kh, kw] in `src_dtype` -> w_packed. */
+int stm_dcn_pack_weight(const StmDcnConv* conv, const void* w_oihw, int32_t src_dtype,
+                        void* w_packed, void* stream);
+
+/* Bytes of scratch the call below needs (may be 0). */
+size_t stm_deform_conv2d_workspace(const StmDcnConv* conv, const StmDcnProblem* probs, int32_t n_probs);
+
+/* y = conv(deform_sample(x, offset) * mask, W) + bias.  bias: float32[out_c] or NULL. */
+int stm_deform_conv2d_fwd(const StmDcnConv* conv, const StmDcnProblem* probs, int32_t n_probs,
+                          const void* w_packed, const float* bias,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Which backend a call with these arguments would run: STM_BACKEND_SIMT / _TCGEN05,
+ * or a negative StmStatus. */
+int stm_deform_conv2d_backend(const StmDcnConv* conv, const StmDcnProblem* probs, int32_t n_probs);
+
+/* FCB(ali) offsets from regressed box deltas (Featurealign.py:46-69), deform_groups = 1:
+ *   shape[b, 0..3, h, w] = (t_x, t_y, t_w, t_h)
+ *   offset[b, 2*(i*kw+j)  ] = 0.1*t_y*kh + (exp(0.2*t_h) - 1) * (i - kh/2)
+ *   offset[b, 2*(i*kw+j)+1] = 0.1*t_x*kw + (exp(0.2*t_w) - 1) * (j - kw/2)
+ * Both tensors are addressed through explicit element strides (n, c, h, w). */
+int stm_fcb_ali_offsets(const void* shape, const int64_t shape_strides[4], int32_t shape_dtype,
+                        void* offset, const int64_t offset_strides[4], int32_t offset_dtype,
+                        int32_t batch, int32_t h, int32_t w, int32_t kernel_h, int32_t kernel_w,
+                        void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Temporal-fusion correlation cost volume                                    */
+/* ------------------------------------------------------------------------- */
+
+enum {
+  STM_CORR_LEAKY_RELU = 1,   /* v = v > 0 ? v : slope * v   (track_to_segment_head.py:62) */
+  STM_CORR_RELU = 2,         /* v = max(v, 0)               (TF_utils.py:31)              */
+  STM_CORR_COPY_FEATS = 4    /* also write relu?(feat_ref), relu?(feat_next) behind the P*P
+                                correlation channels: the 633-channel concat of TF_utils.py:30 */
+};
+
+typedef struct StmCorrDesc {
+  int32_t batch, h, w, c;          /* x1, x2: [batch, h, w, c] NHWC                    */
+  int32_t patch;                   /* patch_size P (odd); output has P*P channels      */
+  int32_t dilation_patch;
+  int32_t dtype;                   /* StmDType of x1, x2                               */
+  int32_t out_dtype;               /* StmDType of out                                  */
+  int32_t flags;                   /* STM_CORR_*                                       */
+  int32_t backend;                 /* StmBackend                                       */
+  float scale;                     /* multiplies the raw dot product (1/C in correlate) */
+  float leaky_slope;               /* 0.1 in correlate                                 */
+  int64_t x1_stride_n, x1_stride_h, x1_stride_w;
+  int64_t x2_stride_n, x2_stride_h, x2_stride_w;
+  /* out[b, k, y, x], k = ph*P + pw  <->  displacement ((ph-P/2)*d, (pw-P/2)*d);
+   * with STM_CORR_COPY_FEATS channels P*P.. hold feat_a then feat_b. */
+  int64_t out_stride_n, out_stride_c, out_stride_h, out_stride_w;
+  /* STM_CORR_COPY_FEATS only: two NHWC tensors with feat_c channels each */
+  int32_t feat_c;
+  int32_t feat_dtype;
+  int64_t feat_a_stride_n, feat_a_stride_h, feat_a_stride_w;
+  int64_t feat_b_stride_n, feat_b_stride_h, feat_b_stride_w;
+} StmCorrDesc;
+
+/* out[b,ph,pw,y,x] = post( scale * sum_c x1[b,y,x,c] * x2[b, y+(ph-r)d, x+(pw-r)d, c] ), zero outside x2. */
+int stm_correlation_fwd(const StmCorrDesc* desc, const void* x1, const void* x2,
+                        const void* feat_a, const void* feat_b, void* out, void* stream);
+
+int stm_correlation_backend(const StmCorrDesc* desc);
+
+/* ------------------------------------------------------------------------- */
+/* Layout helpers (NCHW <-> NHWC with dtype conversion), used at the module   */
+/* boundary when a caller hands over contiguous NCHW tensors.                 */
+/* ------------------------------------------------------------------------- */
+int stm_nchw_to_nhwc(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype,
+                     int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
+int stm_nhwc_to_nchw(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype,
+                     int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
+
+/* ------------------------------------------------------------------------- */
+int stm_version(void);               /* STM_ABI_VERSION of the loaded library            */
+const char* stm_last_error(void);    /* thread-local; "" when the last call succeeded    */
+int stm_device_supported(int32_t device); /* 1 if `device` is compute capability 10.x       */
+/* number of kernels this library has launched from the calling process (bench accounting) */
+uint64_t stm_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STMASK_B200_H_ */

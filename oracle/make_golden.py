@@ -1,0 +1,196 @@
+"""Generate tests/golden/*.npz — run ONCE in the build container (needs /root/reference and
+torchvision CPU); the fixtures are committed and are what the GPU box sees.
+
+    python -m oracle.make_golden
+
+Sources of truth:
+  dcn_torchvision.npz   torchvision.ops.deform_conv2d (CPU, fp32): seeded random cases over kernel
+                        shapes 3x3/3x5/5x3, stride 1/2, dilation, groups, deform_groups, mask, bias
+  dcn_border.npz        border-rule known answers measured on torchvision
+  feature_align.npz     the reference's own FeatureAlign.forward (layers/modules/Featurealign.py:42-74),
+                        FCB(ada) and FCB(ali), imported from /root/reference over the torchvision stand-in
+  correlate.npz         the reference's own correlate() (track_to_segment_head.py:40-62) over the
+                        shifted-product stand-in, P=11, d=1/2
+  backbone_dcn.npz      the reference's ResNetBackbone DCN placement (backbone.py:105-138) for the R50/R101
+                        configs, and a Bottleneck DCN-branch forward (backbone.py:20-26,45)
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import ref_harness as rh
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+DCN_CASES = [
+    # name,            B, Cin, Cout, H,  W,  kh, kw, s, p,      d, groups, dg, mask,  bias
+    ("k3x3",           2, 16,  24,   9,  11, 3,  3,  1, (1, 1), 1, 1,      1,  False, False),
+    ("k3x5",           2, 16,  16,   8,  12, 3,  5,  1, (1, 2), 1, 1,      1,  False, False),
+    ("k5x3",           2, 16,  16,   8,  12, 5,  3,  1, (2, 1), 1, 1,      1,  False, False),
+    ("k5x3_on_3x5",    1, 16,  16,   3,  5,  5,  3,  1, (2, 1), 1, 1,      1,  False, False),
+    ("k3x3_dg4",       2, 32,  16,   7,  9,  3,  3,  1, (1, 1), 1, 1,      4,  False, False),
+    ("k3x5_dg4",       1, 32,  16,   6,  10, 3,  5,  1, (1, 2), 1, 1,      4,  False, False),
+    ("v2_s1",          2, 16,  16,   9,  11, 3,  3,  1, (1, 1), 1, 1,      1,  True,  True),
+    ("v2_s2",          2, 16,  16,   12, 16, 3,  3,  2, (1, 1), 1, 1,      1,  True,  True),
+    ("v2_s2_odd",      1, 16,  24,   11, 15, 3,  3,  2, (1, 1), 1, 1,      1,  True,  True),
+    ("v2_dil2",        1, 16,  16,   10, 10, 3,  3,  1, (2, 2), 2, 1,      1,  True,  True),
+    ("v2_dg2_g2",      1, 16,  16,   8,  8,  3,  3,  1, (1, 1), 1, 2,      2,  True,  True),
+    ("v1_c13_o7",      1, 13,  7,    6,  7,  3,  3,  1, (1, 1), 1, 1,      1,  False, False),
+    ("v1_pad0",        1, 16,  16,   8,  9,  3,  3,  1, (0, 0), 1, 1,      1,  False, False),
+]
+
+
+def _dcn_torchvision():
+    from torchvision.ops import deform_conv2d
+    out = {}
+    meta = {}
+    for idx, (name, B, Cin, Cout, H, W, kh, kw, s, p, d, groups, dg, use_mask, use_bias) in enumerate(DCN_CASES):
+        g = torch.Generator().manual_seed(1000 + idx)
+        Ho = (H + 2 * p[0] - d * (kh - 1) - 1) // s + 1
+        Wo = (W + 2 * p[1] - d * (kw - 1) - 1) // s + 1
+        x = torch.randn(B, Cin, H, W, generator=g)
+        offset = torch.randn(B, dg * 2 * kh * kw, Ho, Wo, generator=g) * 2.0      # N(0, 2^2) px
+        weight = torch.randn(Cout, Cin // groups, kh, kw, generator=g) / (Cin // groups * kh * kw) ** 0.5
+        mask = torch.rand(B, dg * kh * kw, Ho, Wo, generator=g) if use_mask else None
+        bias = torch.randn(Cout, generator=g) if use_bias else None
+        y = deform_conv2d(x, offset, weight, bias, (s, s), p, (d, d), mask)
+        out[f"{name}.x"], out[f"{name}.offset"], out[f"{name}.weight"], out[f"{name}.y"] = (
+            x.numpy(), offset.numpy(), weight.numpy(), y.numpy())
+        if use_mask:
+            out[f"{name}.mask"] = mask.numpy()
+        if use_bias:
+            out[f"{name}.bias"] = bias.numpy()
+        meta[name] = dict(stride=s, padding=list(p), dilation=d, groups=groups, deform_groups=dg)
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "dcn_torchvision.npz"), **out)
+
+
+def _dcn_border():
+    """1x1 kernel on a ramp image, one sample position per case (SURVEY.md Appendix A KATs)."""
+    from torchvision.ops import deform_conv2d
+    H, W = 5, 6
+    x = torch.arange(1, H * W + 1, dtype=torch.float32).view(1, 1, H, W)
+    w = torch.ones(1, 1, 1, 1)
+    positions = [(-0.5, 0.0), (-0.99, 0.0), (-1.0, 0.0), (H - 0.5, 0.0), (float(H), 0.0), (H - 1.0, 0.0),
+                 (0.0, -0.5), (0.0, -1.0), (0.0, W - 0.5), (0.0, float(W)), (1.5, 2.5), (-0.5, -0.5),
+                 (H - 0.5, W - 0.5), (2.25, 3.75), (-3.0, 2.0), (2.0, 40.0)]
+    vals = []
+    for (h, wv) in positions:
+        off = torch.zeros(1, 2, H, W)
+        # output pixel (0,0) samples at (h, w): offset = target - base position (0,0)
+        off[0, 0, 0, 0], off[0, 1, 0, 0] = h, wv
+        y = deform_conv2d(x, off, w)
+        vals.append(float(y[0, 0, 0, 0]))
+    np.savez_compressed(os.path.join(OUT, "dcn_border.npz"), x=x.numpy(),
+                        positions=np.asarray(positions, np.float32), values=np.asarray(vals, np.float32))
+
+
+def _feature_align():
+    fa_mod = rh.load_featurealign()
+    out = {}
+    C = 32
+    cases = [("k3x3", (3, 3), 6, 10), ("k3x5", (3, 5), 6, 10), ("k5x3", (5, 3), 6, 10), ("k5x3_p7", (5, 3), 3, 5)]
+    for mode in ("ada", "ali"):
+        for idx, (name, ks, H, W) in enumerate(cases):
+            torch.manual_seed(2000 + idx + (100 if mode == "ali" else 0))
+            m = fa_mod.FeatureAlign(C, 41, kernel_size=ks, deformable_groups=1, use_pred_offset=(mode == "ada"))
+            if mode == "ada":
+                torch.nn.init.normal_(m.conv_offset.weight, std=0.5)    # non-zero
+            torch.nn.init.normal_(m.conv_adaption.weight, std=(C * ks[0] * ks[1]) ** -0.5)
+            x = torch.randn(2, C, H, W)
+            shape = torch.randn(2, 4, H, W)
+            cap = {}
+            hk = m.conv_adaption.register_forward_hook(
+                lambda mod, inp, o, cap=cap: cap.update(offset=inp[1].detach().clone(), dcn=o.detach().clone()))
+            with torch.no_grad():
+                y = m(x.clone(), shape)
+            hk.remove()
+            key = f"{mode}.{name}"
+            out[f"{key}.x"], out[f"{key}.shape"] = x.numpy(), shape.numpy()
+            out[f"{key}.w_adaption"] = m.conv_adaption.weight.detach().numpy()
+            out[f"{key}.w_conv"], out[f"{key}.b_conv"] = m.conv.weight.detach().numpy(), m.conv.bias.detach().numpy()
+            if mode == "ada":
+                out[f"{key}.w_offset"] = m.conv_offset.weight.detach().numpy()
+            out[f"{key}.offset"] = cap["offset"].numpy()
+            # conv_adaption's output is ReLU-ed in place by the reference (nn.ReLU(inplace=True)),
+            # the hook clones BEFORE that happens
+            out[f"{key}.dcn_relu"] = torch.relu(cap["dcn"]).numpy()
+            out[f"{key}.y"] = y.numpy()
+    np.savez_compressed(os.path.join(OUT, "feature_align.npz"), **out)
+
+
+def _correlate():
+    t2s = rh.load_track_to_segment_head()
+    out = {}
+    for idx, (name, C, H, W, P, d) in enumerate([("p11_d1", 64, 12, 20, 11, 1), ("p11_d2", 64, 12, 20, 11, 2),
+                                                 ("p11_p7", 32, 3, 5, 11, 1), ("p5_d1", 16, 7, 9, 5, 1)]):
+        g = torch.Generator().manual_seed(3000 + idx)
+        x1 = torch.randn(2, C, H, W, generator=g)
+        x2 = torch.randn(2, C, H, W, generator=g)
+        y = t2s.correlate(x1, x2, patch_size=P, dilation_patch=d)
+        out[f"{name}.x1"], out[f"{name}.x2"], out[f"{name}.y"] = x1.numpy(), x2.numpy(), y.numpy()
+        out[f"{name}.pd"] = np.asarray([P, d], np.int32)
+    # the concat + ReLU of TF_utils.py:28-31 on the first case
+    x1, x2 = torch.from_numpy(out["p11_d1.x1"]), torch.from_numpy(out["p11_d1.x2"])
+    g = torch.Generator().manual_seed(3999)
+    t_ref, t_next = torch.randn(2, 24, 12, 20, generator=g), torch.randn(2, 24, 12, 20, generator=g)
+    x_corr = t2s.correlate(x1, x2, patch_size=11)
+    concat = torch.relu(torch.cat([x_corr, t_ref, t_next], dim=1))
+    out["concat.t_ref"], out["concat.t_next"], out["concat.y"] = t_ref.numpy(), t_next.numpy(), concat.numpy()
+    np.savez_compressed(os.path.join(OUT, "correlate.npz"), **out)
+
+
+def _backbone_dcn():
+    bb = rh.load_backbone()
+    out = {}
+    placement = {}
+    for name, args in (("r50", ([3, 4, 6, 3], [0, 4, 6, 3], 2)), ("r101", ([3, 4, 23, 3], [0, 4, 23, 3], 3)),
+                       ("r50_nodcn", ([3, 4, 6, 3],))):
+        net = bb.ResNetBackbone(*args)
+        placement[name] = [[li, bi] for li, layer in enumerate(net.layers) for bi, blk in enumerate(layer) if blk.use_dcn]
+    out["placement"] = np.frombuffer(json.dumps(placement).encode(), dtype=np.uint8)
+    # one stride-1 and one stride-2 Bottleneck with a DCN conv2 (reduced width to keep the fixture small)
+    for name, stride in (("s1", 1), ("s2", 2)):
+        torch.manual_seed(4000 + stride)
+        blk = bb.Bottleneck(64, 16, stride=stride, use_dcn=True,
+                            downsample=torch.nn.Sequential(torch.nn.Conv2d(64, 64, 1, stride=stride, bias=False),
+                                                           torch.nn.BatchNorm2d(64)))
+        blk.eval()
+        dcn = blk.conv2
+        torch.nn.init.normal_(dcn.conv_offset_mask.weight, std=0.05)     # non-zero
+        torch.nn.init.normal_(dcn.conv_offset_mask.bias, std=0.5)
+        torch.nn.init.normal_(dcn.bias, std=0.1)
+        x = torch.randn(2, 64, 10, 14)
+        cap = {}
+        hk = dcn.register_forward_hook(lambda mod, inp, o, cap=cap: cap.update(x=inp[0].detach().clone(),
+                                                                                y=o.detach().clone()))
+        with torch.no_grad():
+            yb = blk(x)
+        hk.remove()
+        out[f"{name}.dcn_x"], out[f"{name}.dcn_y"], out[f"{name}.block_y"] = cap["x"].numpy(), cap["y"].numpy(), yb.numpy()
+        out[f"{name}.weight"], out[f"{name}.bias"] = dcn.weight.detach().numpy(), dcn.bias.detach().numpy()
+        out[f"{name}.com_w"] = dcn.conv_offset_mask.weight.detach().numpy()
+        out[f"{name}.com_b"] = dcn.conv_offset_mask.bias.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "backbone_dcn.npz"), **out)
+
+
+def main():
+    if not rh.available():
+        raise SystemExit("/root/reference is not present: fixtures can only be regenerated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)          # deterministic accumulation order
+    _dcn_torchvision()
+    _dcn_border()
+    _feature_align()
+    _correlate()
+    _backbone_dcn()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

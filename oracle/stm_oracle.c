@@ -1,0 +1,243 @@
+/*
+ * stm_oracle.c — CPU restatement of the STMask hot-path operators.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under stmask_b200/ may import, link or call
+ * this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs use it, and only as the checker or the CPU baseline.
+ *
+ * PARITY PIN STATUS: the reference (MinghanLi/STMask) ships no tests, golden
+ * vectors or fixtures, and the arithmetic of all three operators
+ * lives in third-party CUDA extensions that are NOT under /root/reference and are
+ * not installable offline:
+ *   - dcn_v2            github.com/CharlesShang/DCNv2, unpinned (reference README.md:55-61)
+ *   - mmcv-full==1.1.2  + manual padH/padW patch             (reference README.md:34-38,63-88)
+ *   - spatial-correlation-sampler, pip, unpinned             (reference README.md:50-53)
+ * "parity unpinned" by the reference's own tests.  This restatement follows the
+ * published algorithms of those packages (deformable im2col + GEMM, Dai et al. /
+ * Zhu et al.; FlowNetC-style correlation) and is pinned instead against
+ *   (1) torchvision.ops.deform_conv2d (CPU), an independent implementation of the
+ *       same algorithm that the north star names as the reference CPU path, and
+ *   (2) the reference's own Python call sites (Featurealign.py:42-74,
+ *       track_to_segment_head.py:40-62) imported from /root/reference and run on
+ *       top of (1) — see oracle/make_golden.py and tests/golden/.
+ *
+ * Layouts are the reference's: NCHW float32, contiguous.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Bilinear sample with the deformable-conv border rule:
+ * 0 when h <= -1 or h >= H or w <= -1 or w >= W; otherwise the four neighbours,
+ * each contributing 0 when it lies outside the map.
+ * Follows dmcn_im2col_bilinear / deformable_im2col_bilinear of dcn_v2 and mmcv
+ * (call sites: reference backbone.py:45, Featurealign.py:72). */
+static inline double bilinear_at(const float* plane, int H, int W, double h, double w) {
+  if (!(h > -1.0 && w > -1.0 && h < (double)H && w < (double)W)) return 0.0;
+  int h_low = (int)floor(h), w_low = (int)floor(w);
+  int h_high = h_low + 1, w_high = w_low + 1;
+  double lh = h - h_low, lw = w - w_low, hh = 1.0 - lh, hw = 1.0 - lw;
+  double v1 = (h_low >= 0 && w_low >= 0) ? plane[(size_t)h_low * W + w_low] : 0.0;
+  double v2 = (h_low >= 0 && w_high <= W - 1) ? plane[(size_t)h_low * W + w_high] : 0.0;
+  double v3 = (h_high <= H - 1 && w_low >= 0) ? plane[(size_t)h_high * W + w_low] : 0.0;
+  double v4 = (h_high <= H - 1 && w_high <= W - 1) ? plane[(size_t)h_high * W + w_high] : 0.0;
+  return hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4;
+}
+
+/* Output size of a convolution axis: floor((in + 2p - d(k-1) - 1)/s) + 1. */
+int stm_oracle_out_size(int in, int k, int s, int p, int d) {
+  return (in + 2 * p - d * (k - 1) - 1) / s + 1;
+}
+
+/*
+ * Deformable convolution forward (v1 when mask == NULL, v2 otherwise).
+ *   x      [B, Cin, H, W]
+ *   offset [B, dg*2*kh*kw, Ho, Wo]   channel g*2K + 2k = dy, +1 = dx   (Featurealign.py:67-69)
+ *   mask   [B, dg*kh*kw, Ho, Wo] or NULL (already sigmoid-ed, as dcn_v2_conv receives it)
+ *   weight [Cout, Cin/groups, kh, kw], bias [Cout] or NULL
+ *   y      [B, Cout, Ho, Wo]
+ * Step 1 restates modulated_deformable_im2col (dcn_v2 src/cuda/dcn_v2_im2col_cuda.cu,
+ * mmcv deform_conv_cuda_kernel.cuh): col[(c,i,j), (ho,wo)].  Step 2 is the GEMM
+ * W[Cout, Cin/g*kh*kw] x col, accumulated in double so that the oracle is the
+ * high-precision truth both the fp32 and the bf16 device paths are compared with.
+ * accum64 == 0 switches the GEMM to float accumulation (the cpu_baseline timing leg).
+ */
+int stm_oracle_deform_conv2d(const float* x, const float* offset, const float* mask,
+                             const float* weight, const float* bias, float* y,
+                             int B, int Cin, int H, int W, int Cout, int kh, int kw,
+                             int sh, int sw, int ph, int pw, int dh, int dw,
+                             int groups, int dg, int accum64) {
+  if (groups < 1 || dg < 1 || Cin % groups || Cout % groups || Cin % dg) return -1;
+  const int Ho = stm_oracle_out_size(H, kh, sh, ph, dh);
+  const int Wo = stm_oracle_out_size(W, kw, sw, pw, dw);
+  if (Ho <= 0 || Wo <= 0) return -2;
+  const int K = kh * kw;
+  const int cpg = Cin / groups;       /* input channels per weight group */
+  const int opg = Cout / groups;
+  const int cpd = Cin / dg;           /* input channels per deformable group */
+  const size_t P = (size_t)Ho * Wo;
+  float* col = (float*)malloc(sizeof(float) * (size_t)Cin * K * P);
+  if (!col) return -3;
+
+  for (int b = 0; b < B; ++b) {
+    const float* xb = x + (size_t)b * Cin * H * W;
+    const float* ob = offset ? offset + (size_t)b * dg * 2 * K * P : NULL;
+    const float* mb = mask ? mask + (size_t)b * dg * K * P : NULL;
+    /* ---- deformable im2col ---- */
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < Cin; ++c) {
+      const int g = c / cpd;
+      const float* plane = xb + (size_t)c * H * W;
+      for (int i = 0; i < kh; ++i)
+        for (int j = 0; j < kw; ++j) {
+          const int k = i * kw + j;
+          float* dst = col + ((size_t)c * K + k) * P;
+          for (int ho = 0; ho < Ho; ++ho)
+            for (int wo = 0; wo < Wo; ++wo) {
+              const size_t p = (size_t)ho * Wo + wo;
+              double oy = 0.0, ox = 0.0, m = 1.0;
+              if (ob) {
+                oy = ob[((size_t)g * 2 * K + 2 * k) * P + p];
+                ox = ob[((size_t)g * 2 * K + 2 * k + 1) * P + p];
+              }
+              if (mb) m = mb[((size_t)g * K + k) * P + p];
+              const double h = (double)(ho * sh - ph + i * dh) + oy;
+              const double w = (double)(wo * sw - pw + j * dw) + ox;
+              dst[p] = (float)(bilinear_at(plane, H, W, h, w) * m);
+            }
+        }
+    }
+    /* ---- GEMM per weight group ---- */
+    float* yb = y + (size_t)b * Cout * P;
+#pragma omp parallel for schedule(static)
+    for (int co = 0; co < Cout; ++co) {
+      const int g = co / opg;
+      const float* wrow = weight + (size_t)co * cpg * K;
+      const float* colg = col + (size_t)g * cpg * K * P;
+      float* yrow = yb + (size_t)co * P;
+      const double b0 = bias ? (double)bias[co] : 0.0;
+      if (accum64) {
+        double* acc = (double*)malloc(sizeof(double) * P);
+        for (size_t p = 0; p < P; ++p) acc[p] = b0;
+        for (int kk = 0; kk < cpg * K; ++kk) {
+          const double wv = wrow[kk];
+          const float* crow = colg + (size_t)kk * P;
+          for (size_t p = 0; p < P; ++p) acc[p] += wv * (double)crow[p];
+        }
+        for (size_t p = 0; p < P; ++p) yrow[p] = (float)acc[p];
+        free(acc);
+      } else {
+        for (size_t p = 0; p < P; ++p) yrow[p] = (float)b0;
+        for (int kk = 0; kk < cpg * K; ++kk) {
+          const float wv = wrow[kk];
+          const float* crow = colg + (size_t)kk * P;
+          for (size_t p = 0; p < P; ++p) yrow[p] += wv * crow[p];
+        }
+      }
+    }
+  }
+  free(col);
+  return 0;
+}
+
+/*
+ * Spatial correlation sampler forward, kernel_size = 1, stride = 1, padding = 0,
+ * dilation = 1 (the only configuration the reference uses,
+ * track_to_segment_head.py:53-59):
+ *   out[b, ph, pw, y, x] = sum_c x1[b,c,y,x] * x2[b,c, y+(ph-r)*d, x+(pw-r)*d],  r = P/2,
+ * zero where x2 is indexed outside the map.  Restates correlation_forward of
+ * spatial_correlation_sampler (correlation.cpp / correlation_cuda_kernel.cu), whose
+ * CPU path parallelises over (n, ph) with OpenMP; so does this one.
+ * x1, x2: [B, C, H, W]; out: [B, P, P, H, W].
+ */
+int stm_oracle_correlation(const float* x1, const float* x2, float* out,
+                           int B, int C, int H, int W, int P, int d, int accum64) {
+  if (P < 1 || (P & 1) == 0 || d < 1) return -1;
+  const int r = P / 2;
+  const size_t HW = (size_t)H * W;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b)
+    for (int ph = 0; ph < P; ++ph) {
+      const int dy = (ph - r) * d;
+      double* acc = accum64 ? (double*)malloc(sizeof(double) * W) : NULL;
+      for (int pw = 0; pw < P; ++pw) {
+        const int dx = (pw - r) * d;
+        float* o = out + (((size_t)b * P + ph) * P + pw) * HW;
+        for (int y = 0; y < H; ++y) {
+          const int y2 = y + dy;
+          float* orow = o + (size_t)y * W;
+          if (y2 < 0 || y2 >= H) { memset(orow, 0, sizeof(float) * W); continue; }
+          const int xlo = dx < 0 ? -dx : 0;
+          const int xhi = dx > 0 ? W - dx : W;   /* x in [xlo, xhi) keeps x+dx inside */
+          if (accum64) {
+            for (int x = 0; x < W; ++x) acc[x] = 0.0;
+            for (int c = 0; c < C; ++c) {
+              const float* a = x1 + ((size_t)b * C + c) * HW + (size_t)y * W;
+              const float* bb = x2 + ((size_t)b * C + c) * HW + (size_t)y2 * W + dx;
+              for (int x = xlo; x < xhi; ++x) acc[x] += (double)a[x] * (double)bb[x];
+            }
+            for (int x = 0; x < W; ++x) orow[x] = (x >= xlo && x < xhi) ? (float)acc[x] : 0.f;
+          } else {
+            memset(orow, 0, sizeof(float) * W);
+            for (int c = 0; c < C; ++c) {
+              const float* a = x1 + ((size_t)b * C + c) * HW + (size_t)y * W;
+              const float* bb = x2 + ((size_t)b * C + c) * HW + (size_t)y2 * W + dx;
+              for (int x = xlo; x < xhi; ++x) orow[x] += a[x] * bb[x];
+            }
+          }
+        }
+      }
+      if (acc) free(acc);
+    }
+  return 0;
+}
+
+/*
+ * correlate() post-ops (track_to_segment_head.py:60-62): view as [B, P*P, H, W],
+ * divide by C, in-place leaky-ReLU(0.1).  In place on `out`.
+ */
+void stm_oracle_correlate_post(float* out, size_t n, int C, float slope) {
+  for (size_t i = 0; i < n; ++i) {
+    const float v = out[i] / (float)C;   /* true division, as the reference does */
+    out[i] = v > 0.f ? v : v * slope;
+  }
+}
+
+/*
+ * FCB(ali) offsets (Featurealign.py:46-69), deform_groups = 1.
+ *   shape  [B, 4, H, W] = (t_x, t_y, t_w, t_h)
+ *   offset [B, 2*kh*kw, H, W]; tap (i,j): dy = 0.1*t_y*kh + (exp(0.2*t_h)-1)*(i - kh/2)
+ *                                         dx = 0.1*t_x*kw + (exp(0.2*t_w)-1)*(j - kw/2)
+ * (arange(-k//2+1, k//2+1) = -(k/2) .. k/2 for odd k.)
+ */
+void stm_oracle_fcb_ali_offsets(const float* shape, float* offset, int B, int H, int W, int kh, int kw) {
+  const size_t HW = (size_t)H * W;
+  for (int b = 0; b < B; ++b) {
+    const float* s = shape + (size_t)b * 4 * HW;
+    float* o = offset + (size_t)b * 2 * kh * kw * HW;
+    for (size_t p = 0; p < HW; ++p) {
+      const float tx = s[p], ty = s[HW + p], tw = s[2 * HW + p], th = s[3 * HW + p];
+      const float dx = tx * 0.1f * (float)kw, dy = ty * 0.1f * (float)kh;
+      const float ew = expf(tw * 0.2f) - 1.0f, eh = expf(th * 0.2f) - 1.0f;
+      for (int i = 0; i < kh; ++i)
+        for (int j = 0; j < kw; ++j) {
+          const int k = i * kw + j;
+          const float ri = (float)(i - kh / 2), rj = (float)(j - kw / 2);
+          o[(size_t)(2 * k) * HW + p] = dy + eh * ri;
+          o[(size_t)(2 * k + 1) * HW + p] = dx + ew * rj;
+        }
+    }
+  }
+}
+
+int stm_oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
