@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec of the STMask R101-DCN-FPN FCA+FCB(ada)+TF hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the hot path (stmask_b200/hotpath.py: 11 backbone DCNv2 layers, FCB over P3..P7 for
+the 3 anchor kernels, temporal-fusion correlation+concat) over this rank's frames.  Workload: BASELINE.json
+configs[3] — 36-frame 360x640 clips (padded 384x640), bf16 — two clips (72 frames) per GPU, weak scaling;
+for N > 1 every clip is cut frame-wise across the ranks, so each rank exchanges one-frame feature halos
+(NCCL send/recv) inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIPS_PER_GPU = 2
+FRAMES_PER_CLIP = 36
+METRIC = "frames/sec @360x640 R101 FCA+FCB+TF"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU leg: the reference's CPU path for the same operators on the box's host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_hot_path_frame(hp_cfg, seed=0):
+    """Build the closure that runs ONE frame (+ one TF pair) of the hot path on the CPU: DCN through
+    torchvision.ops.deform_conv2d (the CPU deformable conv the north star names; mmcv-full 1.1.2 / dcn_v2
+    are not installable), correlation through the oracle's OpenMP C port, fp32, all host threads."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from torchvision.ops import deform_conv2d as tv_dcn
+
+    import oracle
+    from stmask_b200 import backbone_dcn
+    from stmask_b200.hotpath import CORR_LEVEL, FPN_CHANNELS, HEAD_KERNELS, fpn_level_sizes
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(seed)
+    shapes = backbone_dcn.dcn_layer_shapes(*hp_cfg.resnet_args, hp_cfg.height, hp_cfg.width)
+    levels = fpn_level_sizes(hp_cfg.height, hp_cfg.width)
+    dcn = []
+    for s in shapes:
+        c = s.channels
+        dcn.append((torch.randn(1, c, s.in_h, s.in_w, generator=g), torch.randn(c, c, 3, 3, generator=g) / (9 * c) ** 0.5,
+                    torch.randn(c, generator=g) * 0.1, torch.randn(27, c, 3, 3, generator=g) * 0.02, torch.randn(27, generator=g) * 0.5, s.stride))
+    fcb = []
+    for kh, kw in HEAD_KERNELS:
+        w = torch.randn(FPN_CHANNELS, FPN_CHANNELS, kh, kw, generator=g) / (FPN_CHANNELS * kh * kw) ** 0.5
+        wo = torch.randn(2 * kh * kw, 4, 1, 1, generator=g) * 0.5
+        fcb.append((w, wo, ((kh - 1) // 2, (kw - 1) // 2)))
+    xs = [torch.randn(1, FPN_CHANNELS, h, w, generator=g) for h, w in levels]
+    boxes = [torch.randn(1, 4, h, w, generator=g) for h, w in levels]
+    h, w = levels[CORR_LEVEL]
+    f1, f2 = (np.random.default_rng(seed).standard_normal((1, FPN_CHANNELS, h, w)).astype(np.float32) for _ in range(2))
+    t1, t2 = torch.randn(1, FPN_CHANNELS, h, w, generator=g), torch.randn(1, FPN_CHANNELS, h, w, generator=g)
+
+    def run():
+        with torch.no_grad():
+            for x, wt, b, wc, bc, st in dcn:
+                out = F.conv2d(x, wc, bc, stride=st, padding=1)
+                tv_dcn(x, out[:, :18], wt, b, (st, st), (1, 1), (1, 1), torch.sigmoid(out[:, 18:]))
+            if hp_cfg.fcb:
+                for wt, wo, pad in fcb:
+                    for x, bx in zip(xs, boxes):
+                        torch.relu_(tv_dcn(x, F.conv2d(bx, wo), wt, None, (1, 1), pad))
+            if hp_cfg.temporal_fusion:
+                corr = oracle.correlate(f1, f2, 11, 1, accum64=False)
+                torch.relu_(torch.cat([torch.from_numpy(corr), t1, t2], 1))
+    return run
+
+
+def cpu_baseline(hp_cfg, budget_s=20.0):
+    run = cpu_hot_path_frame(hp_cfg)
+    run()                                   # warm-up (thread pools, page faults)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        run()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 8:
+            break
+    return {"value": n / dt, "unit": "frames/sec", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{n} frame(s) (+1 TF pair each) of the same hot path, fp32: DCN = torchvision.ops.deform_conv2d CPU "
+                      f"(the reference-side CPU deformable conv named by the north star), correlation = oracle C port (OpenMP); "
+                      f"{dt:.1f} s of CPU work"}
+
+
+def run_reference(args, hp_cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    run = cpu_hot_path_frame(hp_cfg)
+    for _ in range(max(args.warmup, 1)):
+        run()
+    steps = max(args.steps, 1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = time.perf_counter() - t0
+    v = steps / dt
+    cores = os.cpu_count() or 1
+    sample = "each step = 1 frame (+1 TF pair) of the hot path on the host cores, fp32: torchvision.ops.deform_conv2d CPU + oracle C correlation (OpenMP)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/sec", "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{hp_cfg.name()} hot path, 360x640 (padded 384x640), CPU reference path"},
+        "cpu_baseline": {"value": v, "unit": "frames/sec", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frames/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--backbone", default="r101", choices=["r50", "r101"])
+    ap.add_argument("--fcb", default="ada", choices=["ada", "ali", "none"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--clips-per-gpu", type=int, default=CLIPS_PER_GPU)
+    ap.add_argument("--frames-per-clip", type=int, default=FRAMES_PER_CLIP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    import torch
+    from stmask_b200.hotpath import HotPath, HotPathConfig
+
+    hp_cfg = HotPathConfig(backbone=args.backbone, fcb=None if args.fcb == "none" else args.fcb,
+                           dtype=torch.bfloat16 if args.dtype == "bf16" else torch.float32, backend=args.backend)
+    if args.impl == "reference":
+        run_reference(args, hp_cfg)
+        return
+
+    import torch.distributed as dist
+    from stmask_b200 import _lib, ops, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if _lib.lib().stm_device_supported(local_rank) != 1:
+        raise SystemExit("stmask_b200 needs an sm_100 (B200) device; there is no fallback")
+
+    n_clips = args.clips_per_gpu * world
+    plan = sharding.make_plan(n_clips, args.frames_per_clip, world, "frame" if world > 1 else "clip")
+    n_local = plan.local_frames(rank)
+    total_frames = n_clips * args.frames_per_clip
+    hp = HotPath(hp_cfg, dev, seed=0)
+    inp = hp.make_inputs(n_local, dev, seed=rank)
+    in_bytes = sum(t.numel() * t.element_size() for t in inp.values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(x):
+        return hp(x, plan if world > 1 else None, rank)
+
+    for _ in range(args.warmup):
+        out = step(inp)
+    out_bytes = sum(t.numel() * t.element_size() for t in out.values())
+    barrier()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = step(inp)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = total_frames * args.steps / (ms / 1e3)
+
+    # ---------------- per-kernel rooflines (dominant kernel: the FCB deformable conv; plus correlation) ----------
+    peaks = _peaks()
+    roof = corr_roof = None
+    reps = max(5, args.steps)
+    if hp_cfg.fcb:
+        m = hp.fcb[1]                                   # 3x5 kernel, all five levels, one launch
+        xs = [inp[f"fcb.x{l}"] for l in range(5)]
+        offs = [m.offsets(inp[f"fcb.box{l}.1"]) for l in range(5)]
+        spec = m.conv_adaption.spec()
+        wp = m.conv_adaption._cache.weight(m.conv_adaption.weight, spec, xs[0].dtype)
+        outs = ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=args.backend)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        torch.cuda.synchronize()
+        for a, b in evs:
+            a.record()
+            ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=args.backend, outs=outs)
+            b.record()
+        torch.cuda.synchronize()
+        k_ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        px = sum(h * w for h, w in hp.level_sizes)
+        flops = 2.0 * n_local * px * 256 * 256 * 15
+        ach = flops / (k_ms / 1e3) / 1e12
+        be = ops.deform_conv2d_backend(tuple(xs[0].shape), spec, xs[0].dtype, args.backend)
+        roof = {"kernel": f"deform_conv2d[{be}] FCB 3x5 256->256, P3..P7, {n_local} frames, one launch", "bound": "tensor",
+                "achieved": ach, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_burst"],
+                "traffic": None, "ms_per_launch": k_ms, "flops_per_launch": flops,
+                "peak_source": peaks["src"] + ", burst (kernel timed alone)"}
+    if hp_cfg.temporal_fusion:
+        fr, fn = sharding.temporal_pairs(sharding.make_plan(1, n_local, 1), 0, inp["tf.fpn"], None)
+        tr, tn = sharding.temporal_pairs(sharding.make_plan(1, n_local, 1), 0, inp["tf.t2s"], None)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        hp.temporal_fusion(fr, fn, tr, tn)
+        torch.cuda.synchronize()
+        for a, b in evs:
+            a.record()
+            hp.temporal_fusion(fr, fn, tr, tn)
+            b.record()
+        torch.cuda.synchronize()
+        k_ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        es = 2 if hp_cfg.dtype == torch.bfloat16 else 4
+        # the fused kernel also copies the two T2S feature maps into the concat buffer: count those bytes too
+        nbytes = fr.shape[0] * (hp.corr_bytes_per_pair() + 4 * 256 * fr.shape[2] * fr.shape[3] * es)
+        ach = nbytes / (k_ms / 1e3) / 1e9
+        corr_roof = {"kernel": f"correlation+concat[{ops.correlation_backend(tuple(fr.shape), fr.dtype, 11, 1, args.backend)}] "
+                               f"P=11 C=256 24x40, {fr.shape[0]} pairs", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": k_ms,
+                     "bytes_per_launch": nbytes, "peak_source": peaks["src"]}
+
+    # ---------------- end to end: pinned host inputs -> device -> hot path -> host results -----------------------
+    e2e = None
+    if not args.no_e2e:
+        host_in = {k: v.cpu().pin_memory() for k, v in inp.items()}
+        host_out = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in out.items()}
+        del inp, out
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            d_in = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
+            o = step(d_in)
+            for k, v in o.items():
+                host_out[k].copy_(v, non_blocking=True)
+            return o
+
+        e2e_steps = max(2, min(args.steps, 5))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_frames * e2e_steps / float(t_e.item()), "unit": "frames/sec",
+               "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes, "steps": e2e_steps,
+               "note": "through the module API with pinned HOST buffers; per rank per step bytes"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(hp_cfg)
+
+    if rank == 0:
+        fl = hp.flops_per_frame()
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if hp_cfg.dtype == torch.bfloat16 else "f32", "data": "synthetic",
+            "config": {"workload": f"{hp_cfg.name()} hot path (BASELINE.json configs[3]): {args.clips_per_gpu} clips x "
+                                   f"{args.frames_per_clip} frames per GPU, 360x640 padded to 384x640, random weights, non-zero offsets",
+                       "frames_per_step": total_frames, "sharding": plan.mode, "halos_per_rank": len(plan.recv_halos(min(1, world - 1))),
+                       "l2": f"inputs+outputs per step = {(in_bytes + out_bytes) / 1e6:.0f} MB per GPU > 126 MB L2 (no explicit flush needed)",
+                       "dcn_gflop_per_frame": (fl["backbone_dcn"] + fl["fcb"]) / 1e9, "backend": args.backend},
+            "roofline": roof, "roofline_correlation": corr_roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,7 @@
  *                           <- mmcv.ops.DeformConv2d           (layers/modules/Featurealign.py:3,27-31,72)
  *                           <- mmcv.ops.ModulatedDeformConv2d  (named by the north star; same math as dcn_v2)
  *   stm_fcb_ali_offsets     <- the closed-form box->offset map (layers/modules/Featurealign.py:46-69)
+ *   stm_fcb_ada_offsets     <- the 1x1 conv_offset on box deltas    (layers/modules/Featurealign.py:20-25,44)
  *   stm_correlation_fwd     <- spatial_correlation_sampler.spatial_correlation_sample
  *                              + the /C, leaky-ReLU, concat, ReLU that follow it
  *                              (layers/modules/track_to_segment_head.py:53-62,
@@ -37,6 +38,9 @@
 
 #ifdef __cplusplus
 extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
 #define STM_ABI_VERSION 1
@@ -134,6 +138,14 @@ int stm_fcb_ali_offsets(const void* shape, const int64_t shape_strides[4], int32
                         int32_t batch, int32_t h, int32_t w, int32_t kernel_h, int32_t kernel_w,
                         void* stream);
 
+/* FCB(ada) offsets: the bias-free 1x1 `conv_offset` over the 4 box-delta channels
+ * (Featurealign.py:20-25,44).  weight: float32 [out_channels][4] (the conv weight viewed 2-D),
+ * offset[b, o, h, w] = sum_c weight[o][c] * shape[b, c, h, w]. */
+int stm_fcb_ada_offsets(const void* shape, const int64_t shape_strides[4], int32_t shape_dtype,
+                        const float* weight, void* offset, const int64_t offset_strides[4],
+                        int32_t offset_dtype, int32_t batch, int32_t h, int32_t w,
+                        int32_t out_channels, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* Temporal-fusion correlation cost volume                                    */
 /* ------------------------------------------------------------------------- */
@@ -189,6 +201,9 @@ int stm_device_supported(int32_t device); /* 1 if `device` is compute capability
 /* number of kernels this library has launched from the calling process (bench accounting) */
 uint64_t stm_kernel_launch_count(void);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,183 @@
+"""The STMask feature-calibration + temporal-fusion hot path as ONE schedulable unit.
+
+A "step" = one pass over a batch of frames of every operator SURVEY.md §8(a) puts on the path:
+
+  a1/a2  backbone DCNv2 `conv2` of every DCN bottleneck (R50: 7, R101: 11 layers; reference
+         backbone.py:20-26,45,105-138), through the drop-in `dcn_v2.DCN` module (offset/mask
+         predictor + modulated deformable conv);
+  a3/a4  FCB box-guided calibration: for each of the 3 anchor-shaped kernels (3x3, 3x5, 5x3;
+         config.py:657-659) offsets from the regressed box deltas (ada: 1x1 conv, ali: closed form)
+         and relu(DeformConv2d(conf_x, offset)) over the five FPN levels P3..P7 in one grouped
+         launch (Featurealign.py:42-72, prediction_head_FC.py:157-167, shared head STMask.py:91-92);
+  a5/a6  temporal fusion: correlate(fpn_{t-1}, fpn_t) / C, concat with T2S features, ReLU — one
+         kernel — for every consecutive frame pair of a clip (track_to_segment_head.py:40-62,
+         TF_utils.py:28-31), with the previous frame coming from a neighbour rank's halo at a
+         shard boundary (sharding.py).
+
+Everything between these operators (1x1/3x3 dense convs, BN, FPN, the prediction convs) is
+out of scope and is replaced by synthetic activations of the right shape.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import backbone_dcn, ops, sharding
+from .compat.dcn_v2 import DCN
+from .feature_align import FeatureAlign
+
+FPN_STRIDES = (8, 16, 32, 64, 128)
+HEAD_KERNELS = ((3, 3), (3, 5), (5, 3))         # cfg.head_layer_params kernel sizes (config.py:657-659)
+FPN_CHANNELS = 256                               # cfg.fpn.num_features (config.py:364)
+CORR_PATCH = 11                                  # cfg.correlation_patch_size (config.py:690)
+CORR_LEVEL = 1                                   # cfg.correlation_selected_layer (config.py:691)
+NUM_CLASSES = 41
+
+
+def fpn_level_sizes(height: int = 384, width: int = 640) -> List[Tuple[int, int]]:
+    """P3..P7 sizes: C3/C4/C5 strides 8/16/32, then two stride-2 3x3 convs (FPN.py:43-59)."""
+    sizes = []
+    h, w = height, width
+    for _ in range(3):
+        h, w = (h + 1) // 2, (w + 1) // 2
+    for lvl in range(5):
+        if lvl > 0:
+            h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        sizes.append((h, w))
+    return sizes
+
+
+@dataclass
+class HotPathConfig:
+    backbone: str = "r101"             # "r50" | "r101"
+    fcb: Optional[str] = "ada"         # "ada" | "ali" | None (FCA only)
+    temporal_fusion: bool = True
+    height: int = 384                  # 360 padded to a multiple of 32 (config.py:118-120)
+    width: int = 640
+    dtype: torch.dtype = torch.bfloat16
+    backend: str = "auto"
+
+    @property
+    def resnet_args(self):
+        return backbone_dcn.RESNET101_DCN if self.backbone == "r101" else backbone_dcn.RESNET50_DCN
+
+    def name(self) -> str:
+        parts = ["FCA"]
+        if self.fcb:
+            parts.append(f"FCB({self.fcb})")
+        if self.temporal_fusion:
+            parts.append("TF")
+        return f"{'R101' if self.backbone == 'r101' else 'R50'}-DCN-FPN " + "+".join(parts)
+
+
+class HotPath(torch.nn.Module):
+    """Holds the hot path's weights (random, seeded; offset predictors NON-zero) and runs it."""
+
+    def __init__(self, cfg: HotPathConfig, device, seed: int = 0):
+        super().__init__()
+        self.cfg = cfg
+        g = torch.Generator().manual_seed(seed)
+        self.dcn_shapes = backbone_dcn.dcn_layer_shapes(*cfg.resnet_args, cfg.height, cfg.width)
+        self.level_sizes = fpn_level_sizes(cfg.height, cfg.width)
+        self.backbone_dcn = torch.nn.ModuleList()
+        for s in self.dcn_shapes:
+            m = DCN(s.channels, s.channels, kernel_size=3, stride=s.stride, padding=1, dilation=1, deformable_groups=1)
+            k = s.channels * 9
+            with torch.no_grad():
+                m.weight.copy_((torch.rand(m.weight.shape, generator=g) * 2 - 1) / k ** 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+                m.conv_offset_mask.weight.copy_(torch.randn(m.conv_offset_mask.weight.shape, generator=g) * 0.05 / 3)
+                m.conv_offset_mask.bias.copy_(torch.randn(m.conv_offset_mask.bias.shape, generator=g) * 0.5)
+            self.backbone_dcn.append(m)
+        self.fcb = torch.nn.ModuleList()
+        if cfg.fcb:
+            for ks in HEAD_KERNELS:
+                m = FeatureAlign(FPN_CHANNELS, NUM_CLASSES, kernel_size=ks, deformable_groups=1,
+                                 use_pred_offset=(cfg.fcb == "ada"))
+                with torch.no_grad():
+                    m.conv_adaption.weight.copy_(torch.randn(m.conv_adaption.weight.shape, generator=g) /
+                                                 (FPN_CHANNELS * ks[0] * ks[1]) ** 0.5)
+                    if cfg.fcb == "ada":
+                        m.conv_offset.weight.copy_(torch.randn(m.conv_offset.weight.shape, generator=g) * 0.5)
+                self.fcb.append(m)
+        self.to(device=device)
+        # activations / weights of the operators are cfg.dtype; offset predictors' tiny weights stay fp32
+        for m in self.backbone_dcn:
+            m.to(cfg.dtype)
+        for m in self.fcb:
+            m.conv_adaption.to(cfg.dtype)
+
+    # ---------------------------------------------------------------- synthetic activations
+    def make_inputs(self, n_frames: int, device, seed: int = 0, pinned_host: bool = False) -> Dict[str, torch.Tensor]:
+        """Synthetic N(0,1) activations of the shapes the reference produces for `n_frames` frames
+        (NHWC memory, cfg.dtype); box deltas N(0,1) fp32."""
+        g = torch.Generator().manual_seed(1000 + seed)
+        dt = self.cfg.dtype
+
+        def mk(shape, dtype):
+            t = torch.randn(shape, generator=g, dtype=torch.float32).to(dtype).contiguous(memory_format=torch.channels_last)
+            if pinned_host:
+                return t.pin_memory()
+            return t.to(device)
+
+        inp: Dict[str, torch.Tensor] = {}
+        for i, s in enumerate(self.dcn_shapes):
+            inp[f"dcn{i}.x"] = mk((n_frames, s.channels, s.in_h, s.in_w), dt)
+        if self.cfg.fcb:
+            for l, (h, w) in enumerate(self.level_sizes):
+                inp[f"fcb.x{l}"] = mk((n_frames, FPN_CHANNELS, h, w), dt)
+                for k in range(len(HEAD_KERNELS)):
+                    inp[f"fcb.box{l}.{k}"] = mk((n_frames, 4, h, w), torch.float32)
+        if self.cfg.temporal_fusion:
+            h, w = self.level_sizes[CORR_LEVEL]
+            inp["tf.fpn"] = mk((n_frames, FPN_CHANNELS, h, w), dt)
+            inp["tf.t2s"] = mk((n_frames, FPN_CHANNELS, h, w), dt)
+        return inp
+
+    # ---------------------------------------------------------------- the step
+    @torch.no_grad()
+    def forward(self, inp: Dict[str, torch.Tensor], plan: Optional[sharding.ShardPlan] = None, rank: int = 0,
+                group=None) -> Dict[str, torch.Tensor]:
+        out: Dict[str, torch.Tensor] = {}
+        halo = None
+        if self.cfg.temporal_fusion and plan is not None and plan.world_size > 1:
+            # post the halo exchange first so the NVLink transfer overlaps the DCN kernels
+            halo = sharding.exchange_halo(plan, rank, [inp["tf.fpn"], inp["tf.t2s"]], group)
+        for i, m in enumerate(self.backbone_dcn):
+            out[f"dcn{i}.y"] = m(inp[f"dcn{i}.x"])
+        for k, m in enumerate(self.fcb):
+            xs = [inp[f"fcb.x{l}"] for l in range(len(self.level_sizes))]
+            boxes = [inp[f"fcb.box{l}.{k}"] for l in range(len(self.level_sizes))]
+            for l, y in enumerate(m.calibrate_levels(xs, boxes)):
+                out[f"fcb.y{l}.{k}"] = y
+        if self.cfg.temporal_fusion:
+            n = inp["tf.fpn"].shape[0]
+            if plan is None:
+                plan = sharding.make_plan(1, n, 1, "clip")
+            fpn_ref, fpn_next = sharding.temporal_pairs(plan, rank, inp["tf.fpn"], halo[0] if halo else None)
+            t2s_ref, t2s_next = sharding.temporal_pairs(plan, rank, inp["tf.t2s"], halo[1] if halo else None)
+            if fpn_next.shape[0] > 0:
+                out["tf.concat"] = self.temporal_fusion(fpn_ref, fpn_next, t2s_ref, t2s_next)
+        return out
+
+    def temporal_fusion(self, fpn_ref, fpn_next, t2s_ref, t2s_next):
+        from .temporal_fusion import correlate_concat
+        return correlate_concat(fpn_ref, fpn_next, t2s_ref, t2s_next, CORR_PATCH, 1, channels_last=True)
+
+    # ---------------------------------------------------------------- accounting
+    def flops_per_frame(self) -> Dict[str, float]:
+        """Algorithmic DCN flops per frame: 2*Ho*Wo*Cout*Cin*kh*kw, gather not counted."""
+        px = sum(h * w for h, w in self.level_sizes)
+        return {
+            "backbone_dcn": float(sum(s.flops_per_frame for s in self.dcn_shapes)),
+            "fcb": float(sum(2 * px * FPN_CHANNELS * FPN_CHANNELS * kh * kw for kh, kw in HEAD_KERNELS)) if self.cfg.fcb else 0.0,
+        }
+
+    def corr_bytes_per_pair(self) -> float:
+        """Algorithmic correlation bytes per frame pair: H*W*(2*C + P*P)*sizeof."""
+        if not self.cfg.temporal_fusion:
+            return 0.0
+        h, w = self.level_sizes[CORR_LEVEL]
+        return float(h * w * (2 * FPN_CHANNELS + CORR_PATCH * CORR_PATCH) * (2 if self.cfg.dtype == torch.bfloat16 else 4))

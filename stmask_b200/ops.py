@@ -1,0 +1,480 @@
+"""Functional front-end: torch tensors -> the C ABI of libstmask_b200.so.
+
+PyTorch is plumbing here (device memory, streams); the arithmetic is in the CUDA library.
+Every function raises on CPU tensors — there is no CPU implementation and no eager fallback.
+
+Tensor conventions: NCHW-*shaped* tensors in any memory format.  Kernels read
+NHWC, so channels-last tensors are consumed in place; contiguous-NCHW tensors are converted
+once by the library's own layout kernel.  Outputs are channels-last tensors of NCHW shape.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib as L
+
+IntPair = Union[int, Sequence[int]]
+
+_BACKENDS = {"auto": L.BACKEND_AUTO, "simt": L.BACKEND_SIMT, "tcgen05": L.BACKEND_TCGEN05}
+
+
+def _pair(v: IntPair) -> Tuple[int, int]:
+    if isinstance(v, int):
+        return v, v
+    v = tuple(int(i) for i in v)
+    if len(v) == 1:
+        return v[0], v[0]
+    if len(v) != 2:
+        raise ValueError(f"expected an int or a pair, got {v}")
+    return v
+
+
+def _dt(t: torch.Tensor, what: str) -> int:
+    if t.dtype == torch.float32:
+        return L.STM_F32
+    if t.dtype == torch.bfloat16:
+        return L.STM_BF16
+    raise TypeError(f"{what}: dtype {t.dtype} not supported (float32 or bfloat16)")
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{what} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} is on {t.device}: stmask_b200 operators run on CUDA (sm_100a) only; "
+                           f"there is no CPU implementation")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def out_size(n: int, k: int, s: int, p: int, d: int) -> int:
+    return (n + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Return a tensor of the same NCHW shape whose channel stride is 1 (NHWC memory)."""
+    if x.dim() != 4:
+        raise ValueError(f"expected a 4-D NCHW tensor, got {tuple(x.shape)}")
+    n, c, h, w = x.shape
+    if x.numel() > 0 and (c == 1 or x.stride(1) == 1) and x.stride(3) >= c and x.stride(2) >= 0 and x.stride(0) >= 0:
+        return x            # channel stride 1: the kernels take the other three strides explicitly
+    if x.numel() == 0:
+        return x.contiguous(memory_format=torch.channels_last)
+    if x.is_contiguous() and n <= 65535:
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        dt = _dt(x, "x")
+        with torch.cuda.device(x.device):
+            L.check(L.lib().stm_nchw_to_nhwc(x.data_ptr(), dt, y.data_ptr(), dt, n, c, h, w, _stream(x)), "stm_nchw_to_nhwc")
+        return y
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def to_nchw(x: torch.Tensor) -> torch.Tensor:
+    """Contiguous-NCHW copy of a channels-last tensor (library layout kernel)."""
+    if x.is_contiguous():
+        return x
+    n, c, h, w = x.shape
+    if x.is_contiguous(memory_format=torch.channels_last) and n <= 65535 and x.numel() > 0:
+        y = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+        dt = _dt(x, "x")
+        with torch.cuda.device(x.device):
+            L.check(L.lib().stm_nhwc_to_nchw(x.data_ptr(), dt, y.data_ptr(), dt, n, c, h, w, _stream(x)), "stm_nhwc_to_nchw")
+        return y
+    return x.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# deformable convolution
+# --------------------------------------------------------------------------------------------
+class ConvSpec:
+    """Static parameters of one deformable conv (shared by all problems of a launch)."""
+
+    __slots__ = ("in_c", "out_c", "kernel", "stride", "padding", "dilation", "groups", "deform_groups")
+
+    def __init__(self, in_c: int, out_c: int, kernel: IntPair, stride: IntPair = 1, padding: IntPair = 0,
+                 dilation: IntPair = 1, groups: int = 1, deform_groups: int = 1):
+        self.in_c, self.out_c = int(in_c), int(out_c)
+        self.kernel, self.stride = _pair(kernel), _pair(stride)
+        self.padding, self.dilation = _pair(padding), _pair(dilation)
+        self.groups, self.deform_groups = int(groups), int(deform_groups)
+        if self.in_c % self.groups or self.out_c % self.groups:
+            raise ValueError(f"in_channels {in_c} / out_channels {out_c} must be divisible by groups {groups}")
+        if self.in_c % self.deform_groups:
+            raise ValueError(f"in_channels {in_c} must be divisible by deform_groups {deform_groups}")
+
+    def out_hw(self, h: int, w: int) -> Tuple[int, int]:
+        return (out_size(h, self.kernel[0], self.stride[0], self.padding[0], self.dilation[0]),
+                out_size(w, self.kernel[1], self.stride[1], self.padding[1], self.dilation[1]))
+
+    def c_struct(self, dtype: int, offset_dtype: int, flags: int, backend: int) -> L.StmDcnConv:
+        return L.StmDcnConv(self.in_c, self.out_c, self.kernel[0], self.kernel[1], self.stride[0], self.stride[1],
+                            self.padding[0], self.padding[1], self.dilation[0], self.dilation[1], self.groups,
+                            self.deform_groups, dtype, offset_dtype, flags, backend)
+
+
+def pack_weight(weight: torch.Tensor, spec: ConvSpec, dtype: torch.dtype) -> torch.Tensor:
+    """[Co, Ci/g, kh, kw] -> OHWI in `dtype` (one library launch)."""
+    _require_cuda(weight, "weight")
+    exp = (spec.out_c, spec.in_c // spec.groups, spec.kernel[0], spec.kernel[1])
+    if tuple(weight.shape) != exp:
+        raise ValueError(f"weight shape {tuple(weight.shape)} != {exp}")
+    src = weight.detach()
+    if src.dtype not in (torch.float32, torch.bfloat16):
+        src = src.float()
+    src = src.contiguous()
+    packed = torch.empty((spec.out_c, spec.kernel[0], spec.kernel[1], spec.in_c // spec.groups), dtype=dtype, device=weight.device)
+    conv = spec.c_struct(_dt(packed, "packed weight"), L.STM_F32, 0, L.BACKEND_AUTO)
+    with torch.cuda.device(weight.device):
+        L.check(L.lib().stm_dcn_pack_weight(C.byref(conv), src.data_ptr(), _dt(src, "weight"), packed.data_ptr(),
+                                            _stream(weight)), "stm_dcn_pack_weight")
+    return packed
+
+
+class PackedWeightCache:
+    """Packed weights (and fp32 biases) keyed on the parameter's storage + version counter, so a
+    module re-packs only after its weight was modified (optimizer step, load_state_dict)."""
+
+    def __init__(self, max_entries: int = 256):
+        self._w = {}
+        self._b = {}
+        self._max = max_entries
+
+    def weight(self, weight: torch.Tensor, spec: ConvSpec, dtype: torch.dtype) -> torch.Tensor:
+        key = (weight.data_ptr(), weight._version, dtype, weight.device, tuple(weight.shape))
+        hit = self._w.get(key)
+        if hit is None:
+            if len(self._w) >= self._max:
+                self._w.clear()
+            hit = pack_weight(weight, spec, dtype)
+            self._w[key] = hit
+        return hit
+
+    def bias(self, bias: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        if bias is None:
+            return None
+        key = (bias.data_ptr(), bias._version, bias.device, bias.dtype)
+        hit = self._b.get(key)
+        if hit is None:
+            if len(self._b) >= self._max:
+                self._b.clear()
+            hit = bias.detach().float().contiguous()
+            self._b[key] = hit
+        return hit
+
+
+def _check_offset(t: Optional[torch.Tensor], ch: int, b: int, ho: int, wo: int, what: str) -> None:
+    if t is None:
+        return
+    _require_cuda(t, what)
+    if tuple(t.shape) != (b, ch, ho, wo):
+        raise ValueError(f"{what} shape {tuple(t.shape)} != {(b, ch, ho, wo)}")
+
+
+def deform_conv2d_multi(xs: Sequence[torch.Tensor], offsets: Sequence[Optional[torch.Tensor]],
+                        masks: Optional[Sequence[Optional[torch.Tensor]]], w_packed: torch.Tensor,
+                        bias_f32: Optional[torch.Tensor], spec: ConvSpec, *, relu: bool = False,
+                        mask_sigmoid: bool = False, backend: str = "auto",
+                        outs: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+    """One launch over several feature maps that share one weight (e.g. the FPN levels of the
+    shared prediction head, reference STMask.py:91-92 / prediction_head_FC.py:166-167).
+
+    offsets[i] is None for every i  =>  plain convolution through the same kernel.
+    """
+    n = len(xs)
+    if n == 0:
+        return []
+    if n > L.DCN_MAX_PROBLEMS:
+        raise ValueError(f"at most {L.DCN_MAX_PROBLEMS} feature maps per launch, got {n}")
+    if len(offsets) != n or (masks is not None and len(masks) != n):
+        raise ValueError("xs / offsets / masks length mismatch")
+    zero_offset = all(o is None for o in offsets)
+    if not zero_offset and any(o is None for o in offsets):
+        raise ValueError("either every problem has an offset tensor or none has")
+    _require_cuda(w_packed, "packed weight")
+    dev = w_packed.device
+    kh, kw = spec.kernel
+    probs = (L.StmDcnProblem * n)()
+    keep = []
+    ys: List[torch.Tensor] = []
+    xdt = None
+    odt = L.STM_F32
+    have_mask = None
+    for i in range(n):
+        x = xs[i]
+        _require_cuda(x, "x")
+        if x.dim() != 4:
+            raise ValueError(f"x must be 4-D (N, C, H, W), got {tuple(x.shape)}")
+        if x.device != dev:
+            raise ValueError("x and weight are on different devices")
+        if x.shape[1] != spec.in_c:
+            raise ValueError(f"x has {x.shape[1]} channels, conv expects {spec.in_c}")
+        d = _dt(x, "x")
+        if xdt is None:
+            xdt = d
+            if w_packed.dtype != x.dtype:
+                raise TypeError(f"packed weight dtype {w_packed.dtype} != x dtype {x.dtype}")
+        elif d != xdt:
+            raise TypeError("all feature maps of one launch must share a dtype")
+        b, _, h, w = x.shape
+        ho, wo = spec.out_hw(h, w)
+        if ho <= 0 or wo <= 0:
+            raise ValueError(f"convolution output size would be {ho}x{wo}")
+        xn = to_nhwc(x)
+        off = offsets[i]
+        msk = masks[i] if masks is not None else None
+        if have_mask is None:
+            have_mask = msk is not None
+        elif have_mask != (msk is not None):
+            raise ValueError("either every problem has a mask or none has")
+        _check_offset(off, spec.deform_groups * 2 * kh * kw, b, ho, wo, "offset")
+        _check_offset(msk, spec.deform_groups * kh * kw, b, ho, wo, "mask")
+        first = off if off is not None else msk
+        if first is not None:
+            d_off = _dt(first, "offset")
+            if not keep:
+                odt = d_off
+            elif d_off != odt:
+                raise TypeError("all offsets / masks of one launch must share a dtype")
+            if msk is not None and msk.dtype != first.dtype:
+                msk = msk.to(first.dtype)
+        if outs is not None:
+            y = outs[i]
+            if tuple(y.shape) != (b, spec.out_c, ho, wo) or y.dtype != x.dtype or not (spec.out_c == 1 or y.stride(1) == 1):
+                raise ValueError("preallocated output must be a channels-last tensor of the right shape/dtype")
+        else:
+            y = torch.empty((b, spec.out_c, ho, wo), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
+        keep += [xn, off, msk, y]
+        ys.append(y)
+        p = probs[i]
+        p.batch, p.in_h, p.in_w, p.out_h, p.out_w = b, h, w, ho, wo
+        p.x = xn.data_ptr()
+        p.x_stride_n, p.x_stride_h, p.x_stride_w = xn.stride(0), xn.stride(2), xn.stride(3)
+        if off is not None:
+            p.offset = off.data_ptr()
+            p.off_stride_n, p.off_stride_c, p.off_stride_h, p.off_stride_w = off.stride()
+        if msk is not None:
+            p.mask = msk.data_ptr()
+            p.mask_stride_n, p.mask_stride_c, p.mask_stride_h, p.mask_stride_w = msk.stride()
+        p.y = y.data_ptr()
+        p.y_stride_n, p.y_stride_h, p.y_stride_w = y.stride(0), y.stride(2), y.stride(3)
+    flags = (L.DCN_RELU if relu else 0) | (L.DCN_MASK_SIGMOID if mask_sigmoid else 0) | (L.DCN_ZERO_OFFSET if zero_offset else 0)
+    conv = spec.c_struct(xdt, odt, flags, _BACKENDS[backend])
+    if bias_f32 is not None:
+        _require_cuda(bias_f32, "bias")
+        if bias_f32.dtype != torch.float32 or tuple(bias_f32.shape) != (spec.out_c,) or not bias_f32.is_contiguous():
+            raise ValueError("bias must be a contiguous float32 [out_channels] tensor")
+    lib = L.lib()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.stm_deform_conv2d_workspace(C.byref(conv), probs, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+        rc = lib.stm_deform_conv2d_fwd(C.byref(conv), probs, n, w_packed.data_ptr(),
+                                       bias_f32.data_ptr() if bias_f32 is not None else None,
+                                       ws.data_ptr() if ws is not None else None, ws_bytes,
+                                       torch.cuda.current_stream(dev).cuda_stream)
+    L.check(rc, "stm_deform_conv2d_fwd")
+    return ys
+
+
+def deform_conv2d_backend(x_shape: Sequence[int], spec: ConvSpec, dtype: torch.dtype, backend: str = "auto") -> str:
+    """Which kernel family a call would use ('simt' / 'tcgen05') — shape-only query."""
+    b, _, h, w = x_shape
+    ho, wo = spec.out_hw(h, w)
+    prob = (L.StmDcnProblem * 1)()
+    p = prob[0]
+    p.batch, p.in_h, p.in_w, p.out_h, p.out_w = b, h, w, ho, wo
+    p.x = p.y = p.offset = 256           # dummy non-null, 256-byte aligned addresses; never dereferenced here
+    p.x_stride_w, p.x_stride_h, p.x_stride_n = spec.in_c, spec.in_c * w, spec.in_c * w * h
+    p.y_stride_w, p.y_stride_h, p.y_stride_n = spec.out_c, spec.out_c * wo, spec.out_c * wo * ho
+    dt = L.STM_F32 if dtype == torch.float32 else L.STM_BF16
+    conv = spec.c_struct(dt, L.STM_F32, 0, _BACKENDS[backend])
+    rc = L.lib().stm_deform_conv2d_backend(C.byref(conv), prob, 1)
+    if rc < 0:
+        L.check(rc, "stm_deform_conv2d_backend")
+    return L.BACKEND_NAMES[rc]
+
+
+def deform_conv2d(x: torch.Tensor, offset: Optional[torch.Tensor], weight: torch.Tensor,
+                  bias: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, stride: IntPair = 1,
+                  padding: IntPair = 0, dilation: IntPair = 1, groups: int = 1, deform_groups: int = 1, *,
+                  relu: bool = False, mask_sigmoid: bool = False, backend: str = "auto",
+                  cache: Optional[PackedWeightCache] = None) -> torch.Tensor:
+    """DCNv1 (mask None) / DCNv2 forward with an OIHW weight (packed on the fly or via `cache`)."""
+    _require_cuda(x, "x")
+    _require_cuda(weight, "weight")
+    spec = ConvSpec(x.shape[1] if x.dim() == 4 else -1, weight.shape[0], weight.shape[2:], stride, padding, dilation,
+                    groups, deform_groups)
+    cache = cache or PackedWeightCache()
+    wp = cache.weight(weight, spec, x.dtype)
+    bf = cache.bias(bias)
+    return deform_conv2d_multi([x], [offset], [mask] if mask is not None else None, wp, bf, spec, relu=relu,
+                               mask_sigmoid=mask_sigmoid, backend=backend)[0]
+
+
+def fcb_ali_offsets(shape: torch.Tensor, kernel_size: IntPair, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Closed-form FCB(ali) offsets from box deltas (reference Featurealign.py:46-69)."""
+    _require_cuda(shape, "shape")
+    if shape.dim() != 4 or shape.shape[1] != 4:
+        raise ValueError(f"shape must be [B, 4, H, W], got {tuple(shape.shape)}")
+    kh, kw = _pair(kernel_size)
+    b, _, h, w = shape.shape
+    off = torch.empty((b, 2 * kh * kw, h, w), dtype=dtype or shape.dtype, device=shape.device)
+    if off.numel() == 0:
+        return off
+    ss = (C.c_int64 * 4)(*shape.stride())
+    os_ = (C.c_int64 * 4)(*off.stride())
+    with torch.cuda.device(shape.device):
+        L.check(L.lib().stm_fcb_ali_offsets(shape.data_ptr(), ss, _dt(shape, "shape"), off.data_ptr(), os_, _dt(off, "offset"),
+                                            b, h, w, kh, kw, _stream(shape)), "stm_fcb_ali_offsets")
+    return off
+
+
+def fcb_ada_offsets(shape: torch.Tensor, weight: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """FCB(ada) offsets: the bias-free 1x1 `conv_offset` applied to the box deltas
+    (reference Featurealign.py:20-25,44).  weight: [OC, 4, 1, 1]."""
+    _require_cuda(shape, "shape")
+    _require_cuda(weight, "conv_offset.weight")
+    if shape.dim() != 4 or shape.shape[1] != 4:
+        raise ValueError(f"shape must be [B, 4, H, W], got {tuple(shape.shape)}")
+    if weight.dim() != 4 or tuple(weight.shape[1:]) != (4, 1, 1):
+        raise ValueError(f"conv_offset.weight must be [OC, 4, 1, 1], got {tuple(weight.shape)}")
+    b, _, h, w = shape.shape
+    oc = weight.shape[0]
+    w2 = weight.detach().reshape(oc, 4).float().contiguous()
+    off = torch.empty((b, oc, h, w), dtype=dtype or shape.dtype, device=shape.device)
+    if off.numel() == 0:
+        return off
+    ss = (C.c_int64 * 4)(*shape.stride())
+    os_ = (C.c_int64 * 4)(*off.stride())
+    with torch.cuda.device(shape.device):
+        L.check(L.lib().stm_fcb_ada_offsets(shape.data_ptr(), ss, _dt(shape, "shape"), w2.data_ptr(), off.data_ptr(), os_,
+                                            _dt(off, "offset"), b, h, w, oc, _stream(shape)), "stm_fcb_ada_offsets")
+    return off
+
+
+# --------------------------------------------------------------------------------------------
+# correlation
+# --------------------------------------------------------------------------------------------
+def correlation(x1: torch.Tensor, x2: torch.Tensor, patch_size: int = 11, dilation_patch: int = 1, *,
+                scale: float = 1.0, leaky_slope: Optional[float] = None, relu: bool = False,
+                feats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, out_dtype: Optional[torch.dtype] = None,
+                channels_last: bool = False, backend: str = "auto") -> torch.Tensor:
+    """Cost volume [B, P*P, H, W] (+ 2*feat_c concat channels when `feats` is given).
+
+    out[b, ph*P+pw, y, x] = post(scale * <x1[b,:,y,x], x2[b,:,y+(ph-r)d, x+(pw-r)d]>), zero outside x2.
+    `channels_last=True` returns NHWC memory (what the RoIAlign/TemporalNet convs want);
+    the default is contiguous NCHW so that the reference's `.view(b, ph*pw, h, w)` works.
+    """
+    _require_cuda(x1, "input1")
+    _require_cuda(x2, "input2")
+    if x1.dim() != 4 or x1.shape != x2.shape:
+        raise ValueError(f"input1/input2 must be 4-D of equal shape, got {tuple(x1.shape)} and {tuple(x2.shape)}")
+    if x1.dtype != x2.dtype or x1.device != x2.device:
+        raise TypeError("input1/input2 dtype or device mismatch")
+    P, d = int(patch_size), int(dilation_patch)
+    if P < 1 or P % 2 == 0:
+        raise ValueError(f"patch_size must be odd and positive, got {P}")
+    if d < 1:
+        raise ValueError("dilation_patch must be >= 1")
+    b, c, h, w = x1.shape
+    a, bb = to_nhwc(x1), to_nhwc(x2)
+    flags = 0
+    fa = fb = None
+    fc = 0
+    fdt = L.STM_BF16
+    if leaky_slope is not None:
+        flags |= L.CORR_LEAKY_RELU
+    if relu:
+        flags |= L.CORR_RELU
+    if feats is not None:
+        fa, fb = feats
+        _require_cuda(fa, "feat_a")
+        _require_cuda(fb, "feat_b")
+        if fa.shape != fb.shape or fa.dim() != 4 or fa.shape[0] != b or tuple(fa.shape[2:]) != (h, w) or fa.dtype != fb.dtype:
+            raise ValueError("feats must be two [B, Cf, H, W] tensors matching the inputs' batch and size")
+        fa, fb = to_nhwc(fa), to_nhwc(fb)
+        fc = fa.shape[1]
+        fdt = _dt(fa, "feats")
+        flags |= L.CORR_COPY_FEATS
+    odt = out_dtype or x1.dtype
+    ch = P * P + 2 * fc
+    out = torch.empty((b, ch, h, w), dtype=odt, device=x1.device,
+                      memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    if out.numel() == 0:
+        return out
+    desc = L.StmCorrDesc()
+    desc.batch, desc.h, desc.w, desc.c = b, h, w, c
+    desc.patch, desc.dilation_patch = P, d
+    desc.dtype, desc.out_dtype = _dt(a, "input1"), _dt(out, "out")
+    desc.flags, desc.backend = flags, _BACKENDS[backend]
+    desc.scale, desc.leaky_slope = float(scale), float(leaky_slope or 0.0)
+    desc.x1_stride_n, desc.x1_stride_h, desc.x1_stride_w = a.stride(0), a.stride(2), a.stride(3)
+    desc.x2_stride_n, desc.x2_stride_h, desc.x2_stride_w = bb.stride(0), bb.stride(2), bb.stride(3)
+    desc.out_stride_n, desc.out_stride_c, desc.out_stride_h, desc.out_stride_w = out.stride()
+    desc.feat_c, desc.feat_dtype = fc, fdt
+    if fa is not None:
+        desc.feat_a_stride_n, desc.feat_a_stride_h, desc.feat_a_stride_w = fa.stride(0), fa.stride(2), fa.stride(3)
+        desc.feat_b_stride_n, desc.feat_b_stride_h, desc.feat_b_stride_w = fb.stride(0), fb.stride(2), fb.stride(3)
+    with torch.cuda.device(x1.device):
+        rc = L.lib().stm_correlation_fwd(C.byref(desc), a.data_ptr(), bb.data_ptr(),
+                                         fa.data_ptr() if fa is not None else None,
+                                         fb.data_ptr() if fb is not None else None, out.data_ptr(), _stream(x1))
+    L.check(rc, "stm_correlation_fwd")
+    return out
+
+
+def correlation_backend(shape: Sequence[int], dtype: torch.dtype, patch_size: int = 11, dilation_patch: int = 1,
+                        backend: str = "auto") -> str:
+    b, c, h, w = shape
+    desc = L.StmCorrDesc()
+    desc.batch, desc.h, desc.w, desc.c = b, h, w, c
+    desc.patch, desc.dilation_patch = patch_size, dilation_patch
+    desc.dtype = desc.out_dtype = L.STM_F32 if dtype == torch.float32 else L.STM_BF16
+    desc.backend = _BACKENDS[backend]
+    desc.x1_stride_w = desc.x2_stride_w = c
+    desc.x1_stride_h = desc.x2_stride_h = c * w
+    desc.x1_stride_n = desc.x2_stride_n = c * w * h
+    desc.out_stride_w, desc.out_stride_h, desc.out_stride_c = 1, w, h * w
+    desc.out_stride_n = h * w * patch_size * patch_size
+    rc = L.lib().stm_correlation_backend(C.byref(desc))
+    if rc < 0:
+        L.check(rc, "stm_correlation_backend")
+    return L.BACKEND_NAMES[rc]
+
+
+# --------------------------------------------------------------------------------------------
+# torch.library registration (CUDA key only, fake impl for shape inference, no CPU key)
+# --------------------------------------------------------------------------------------------
+_op_cache = PackedWeightCache()
+
+
+@torch.library.custom_op("stmask_b200::deform_conv2d", mutates_args=(), device_types="cuda")
+def _deform_conv2d_op(x: torch.Tensor, offset: torch.Tensor, mask: Optional[torch.Tensor], weight: torch.Tensor,
+                      bias: Optional[torch.Tensor], stride: List[int], padding: List[int], dilation: List[int],
+                      groups: int, deform_groups: int, relu: bool, mask_sigmoid: bool) -> torch.Tensor:
+    return deform_conv2d(x, offset, weight, bias, mask, stride, padding, dilation, groups, deform_groups, relu=relu,
+                         mask_sigmoid=mask_sigmoid, cache=_op_cache)
+
+
+@_deform_conv2d_op.register_fake
+def _(x, offset, mask, weight, bias, stride, padding, dilation, groups, deform_groups, relu, mask_sigmoid):
+    spec = ConvSpec(x.shape[1], weight.shape[0], weight.shape[2:], stride, padding, dilation, groups, deform_groups)
+    ho, wo = spec.out_hw(x.shape[2], x.shape[3])
+    return torch.empty((x.shape[0], weight.shape[0], ho, wo), dtype=x.dtype, device=x.device,
+                       memory_format=torch.channels_last)
+
+
+@torch.library.custom_op("stmask_b200::correlation", mutates_args=(), device_types="cuda")
+def _correlation_op(x1: torch.Tensor, x2: torch.Tensor, patch_size: int, dilation_patch: int, scale: float,
+                    leaky_slope: float, relu: bool) -> torch.Tensor:
+    return correlation(x1, x2, patch_size, dilation_patch, scale=scale,
+                       leaky_slope=leaky_slope if leaky_slope != 0.0 else None, relu=relu)
+
+
+@_correlation_op.register_fake
+def _(x1, x2, patch_size, dilation_patch, scale, leaky_slope, relu):
+    return x1.new_empty((x1.shape[0], patch_size * patch_size, x1.shape[2], x1.shape[3]))

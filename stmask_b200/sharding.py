@@ -1,0 +1,192 @@
+"""Clip / frame sharding of the hot path over the GPUs of one box, and the one-frame feature
+halo that temporal fusion needs at shard boundaries.
+
+The reference is single-GPU, batch 1, strictly sequential (eval.py:590-605, track_TF.py:43-54);
+there is nothing to port.  Backbone DCN and FCB are per-frame independent; the correlation for
+frame t reads frame t-1's `{fpn_feat, T2S_feat}` (TF_utils.py:22-31).  So the only exchange is:
+rank r sends the features of its LAST local frame of a clip to the rank that owns the NEXT frame
+of that clip.  Point-to-point `isend/irecv` (NCCL send/recv over NVLink on GPUs, gloo in the CPU
+tests), all boundaries of a step batched into one message per neighbour; no all-reduce.
+
+One process per GPU; `torch.distributed` is plumbing.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class Segment:
+    """A run of consecutive frames of one clip owned by one rank."""
+    clip: int
+    start: int       # first frame (inclusive), index within the clip
+    stop: int        # last frame (exclusive)
+    offset: int      # position of `start` in the rank's local frame batch
+
+    @property
+    def length(self) -> int:
+        return self.stop - self.start
+
+
+@dataclass(frozen=True)
+class Halo:
+    """Rank `src` owns frame `frame-1` of `clip`, rank `dst` owns `frame`."""
+    clip: int
+    frame: int
+    src: int
+    dst: int
+
+
+@dataclass
+class ShardPlan:
+    world_size: int
+    n_clips: int
+    frames_per_clip: int
+    mode: str
+    segments: List[List[Segment]]         # per rank
+    halos: List[Halo]
+
+    def local_frames(self, rank: int) -> int:
+        return sum(s.length for s in self.segments[rank])
+
+    def recv_halos(self, rank: int) -> List[Halo]:
+        return [h for h in self.halos if h.dst == rank]
+
+    def send_halos(self, rank: int) -> List[Halo]:
+        return [h for h in self.halos if h.src == rank]
+
+    def local_pairs(self, rank: int) -> int:
+        """(t-1, t) frame pairs whose frame t is local: every local frame that is not a clip start."""
+        return sum(s.length - (1 if s.start == 0 else 0) for s in self.segments[rank])
+
+
+def make_plan(n_clips: int, frames_per_clip: int, world_size: int, mode: str = "clip") -> ShardPlan:
+    """`clip`:  flatten (clip, frame) and cut into `world_size` contiguous ranges (whole clips per rank
+                when n_clips % world_size == 0  =>  no halo at all).
+       `frame`: every clip's frames are cut into `world_size` contiguous ranges (rank r owns the r-th
+                range of EVERY clip  =>  world_size-1 boundaries per clip); this is the layout that
+                exercises the halo exchange."""
+    if n_clips < 0 or frames_per_clip < 1 or world_size < 1:
+        raise ValueError("bad plan arguments")
+    if mode not in ("clip", "frame"):
+        raise ValueError(f"unknown sharding mode {mode!r}")
+    segs: List[List[Segment]] = [[] for _ in range(world_size)]
+    owner: Dict[Tuple[int, int], int] = {}
+
+    def add(rank: int, clip: int, a: int, b: int):
+        if b <= a:
+            return
+        off = sum(s.length for s in segs[rank])
+        segs[rank].append(Segment(clip, a, b, off))
+        for f in range(a, b):
+            owner[(clip, f)] = rank
+
+    if mode == "clip":
+        total = n_clips * frames_per_clip
+        for r in range(world_size):
+            lo, hi = r * total // world_size, (r + 1) * total // world_size
+            f = lo
+            while f < hi:
+                clip, a = divmod(f, frames_per_clip)
+                b = min(frames_per_clip, a + (hi - f))
+                add(r, clip, a, b)
+                f += b - a
+    else:
+        for clip in range(n_clips):
+            for r in range(world_size):
+                add(r, clip, r * frames_per_clip // world_size, (r + 1) * frames_per_clip // world_size)
+    halos = []
+    for r in range(world_size):
+        for s in segs[r]:
+            if s.start > 0:
+                src = owner[(s.clip, s.start - 1)]
+                if src != r:
+                    halos.append(Halo(s.clip, s.start, src, r))
+    return ShardPlan(world_size, n_clips, frames_per_clip, mode, segs, halos)
+
+
+def exchange_halo(plan: ShardPlan, rank: int, feats: Sequence[torch.Tensor], group=None) -> List[Optional[torch.Tensor]]:
+    """Send the last-frame features of every local segment that another rank continues, receive the
+    halos this rank needs.  `feats` = per-frame feature tensors of the local batch, each
+    [n_local, C, H, W] (e.g. fpn_feat and T2S_feat); they are packed into ONE message per
+    neighbour, NHWC on the wire: [n_boundaries, H, W, sum(C)].
+
+    Returns, for each f in feats, a tensor [n_recv, C, H, W] ordered like plan.recv_halos(rank)
+    (None when this rank receives nothing).  All isend/irecv of the step go out in one batch."""
+    sends = plan.send_halos(rank)
+    recvs = plan.recv_halos(rank)
+    if plan.world_size == 1 or (not sends and not recvs):
+        return [None for _ in feats]
+    ref = feats[0]
+    chans = [f.shape[1] for f in feats]
+    hw = tuple(ref.shape[2:])
+    # wire format: [n_boundaries, H, W, sum(C)] contiguous == the kernels' NHWC layout, whatever the
+    # local memory format is (P2P ops need contiguous buffers; both sides must agree)
+    seg_of = {(s.clip, s.stop): s for s in plan.segments[rank]}
+    ops_, keep = [], []
+    by_dst: Dict[int, List[Halo]] = {}
+    for h in sends:
+        by_dst.setdefault(h.dst, []).append(h)
+    for dst, hs in sorted(by_dst.items()):
+        idx = [seg_of[(h.clip, h.frame)].offset + seg_of[(h.clip, h.frame)].length - 1 for h in hs]
+        idx_t = torch.as_tensor(idx, device=ref.device)
+        msg = torch.cat([f.index_select(0, idx_t).permute(0, 2, 3, 1) for f in feats], dim=3).contiguous()
+        keep.append(msg)
+        ops_.append(dist.P2POp(dist.isend, msg, dst, group))
+    by_src: Dict[int, List[Halo]] = {}
+    for h in recvs:
+        by_src.setdefault(h.src, []).append(h)
+    bufs: Dict[int, torch.Tensor] = {}
+    for src, hs in sorted(by_src.items()):
+        buf = torch.empty((len(hs),) + hw + (sum(chans),), dtype=ref.dtype, device=ref.device)
+        bufs[src] = buf
+        ops_.append(dist.P2POp(dist.irecv, buf, src, group))
+    for w in dist.batch_isend_irecv(ops_):
+        w.wait()
+    if not recvs:
+        return [None for _ in feats]
+    # reorder to plan.recv_halos(rank) order
+    pos = {}
+    for src, hs in by_src.items():
+        for i, h in enumerate(hs):
+            pos[(h.clip, h.frame)] = (src, i)
+    rows = [bufs[pos[(h.clip, h.frame)][0]][pos[(h.clip, h.frame)][1]] for h in recvs]
+    stacked = rows[0].new_empty((len(rows),) + tuple(rows[0].shape)) if len(by_src) > 1 else None
+    if stacked is None:
+        src0 = next(iter(by_src))
+        order = [pos[(h.clip, h.frame)][1] for h in recvs]
+        stacked = bufs[src0] if order == list(range(len(order))) else bufs[src0][order]
+    else:
+        torch.stack(rows, 0, out=stacked)
+    nchw = stacked.permute(0, 3, 1, 2)          # NCHW-shaped view of NHWC memory (channels-last)
+    out, c0 = [], 0
+    for c in chans:
+        out.append(nchw[:, c0:c0 + c])
+        c0 += c
+    return out
+
+
+def temporal_pairs(plan: ShardPlan, rank: int, feat: torch.Tensor, halo: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(ref, next) batches for the correlation of this rank: next = every local frame that is not a
+    clip start; ref = the frame before it — local, or the received halo at a shard boundary.
+    Mirrors the train-time batched call (STMask.py:289-297: ref = frames[::2], next = frames[1::2])
+    generalised to clips of any length."""
+    recvs = plan.recv_halos(rank)
+    halo_row = {(h.clip, h.frame): i for i, h in enumerate(recvs)}
+    ref_idx, next_idx = [], []
+    n_local = plan.local_frames(rank)
+    for s in plan.segments[rank]:
+        for f in range(s.start, s.stop):
+            if f == 0:
+                continue
+            loc = s.offset + (f - s.start)
+            next_idx.append(loc)
+            ref_idx.append(loc - 1 if f > s.start else n_local + halo_row[(s.clip, f)])
+    src = feat if halo is None else torch.cat([feat, halo.to(feat.dtype)], 0)
+    dev = feat.device
+    return (src.index_select(0, torch.as_tensor(ref_idx, device=dev, dtype=torch.long)),
+            feat.index_select(0, torch.as_tensor(next_idx, device=dev, dtype=torch.long)))

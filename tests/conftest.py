@@ -8,6 +8,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+SHIMS = os.path.join(ROOT, "shims")       # `import dcn_v2`, `import mmcv.ops`, `import spatial_correlation_sampler`
+if SHIMS not in sys.path:
+    sys.path.insert(0, SHIMS)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 

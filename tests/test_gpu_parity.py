@@ -1,0 +1,375 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-facing Python API)
+against the CPU oracle and the committed golden vectors.
+
+Tolerances are the north star's: <= 1e-4 relative in fp32, <= 1e-2 in bf16, where relative
+error is max|got - want| / max|want| over a feature tensor (conftest.rel_err).  For bf16 the
+inputs are rounded to bf16 first and the oracle runs on the rounded values, so the figure
+measures the kernel's arithmetic, not the input quantisation.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import golden_meta, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-4, torch.bfloat16: 1e-2}
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def _ops():
+    from stmask_b200 import ops
+    return ops
+
+
+def q(a, dtype):
+    """numpy fp32 -> numpy fp32 rounded to `dtype`."""
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dtype).float().numpy()
+
+
+def dev(a, dtype, device, channels_last=False):
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device=device, dtype=dtype)
+    if channels_last and t.dim() == 4:
+        t = t.contiguous(memory_format=torch.channels_last)
+    return t
+
+
+def run_dcn(device, dtype, x, offset, weight, bias=None, mask=None, backend="auto", channels_last=True,
+            offset_dtype=torch.float32, **kw):
+    ops = _ops()
+    y = ops.deform_conv2d(dev(x, dtype, device, channels_last), dev(offset, offset_dtype, device) if offset is not None else None,
+                          dev(weight, dtype, device), dev(bias, torch.float32, device) if bias is not None else None,
+                          dev(mask, offset_dtype, device) if mask is not None else None, backend=backend, **kw)
+    torch.cuda.synchronize()
+    return y.float().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------
+# deformable conv vs golden vectors (torchvision CPU) and vs the oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dcn_golden_torchvision(cuda_device, dtype):
+    z = load_golden("dcn_torchvision.npz")
+    for name, m in golden_meta(z).items():
+        x, w = q(z[f"{name}.x"], dtype), q(z[f"{name}.weight"], dtype)
+        bias = z[f"{name}.bias"] if f"{name}.bias" in z else None
+        mask = z[f"{name}.mask"] if f"{name}.mask" in z else None
+        kw = dict(stride=m["stride"], padding=m["padding"], dilation=m["dilation"], groups=m["groups"],
+                  deform_groups=m["deform_groups"])
+        got = run_dcn(cuda_device, dtype, x, z[f"{name}.offset"], w, bias, mask, **kw)
+        want = z[f"{name}.y"] if dtype == torch.float32 else oracle.deform_conv2d(x, z[f"{name}.offset"], w, bias, mask, **kw)
+        assert got.shape == want.shape, name
+        assert rel_err(got, want) <= TOL[dtype], (name, rel_err(got, want))
+
+
+def test_dcn_border_rule(cuda_device):
+    z = load_golden("dcn_border.npz")
+    x = z["x"]
+    H, W = x.shape[2:]
+    w = np.ones((1, 1, 1, 1), np.float32)
+    for (h, wv), want in zip(z["positions"], z["values"]):
+        off = np.zeros((1, 2, H, W), np.float32)
+        off[0, 0, 0, 0], off[0, 1, 0, 0] = h, wv
+        got = run_dcn(cuda_device, torch.float32, x, off, w)[0, 0, 0, 0]
+        assert abs(got - want) <= 1e-5 * max(1.0, abs(want)), (h, wv, got, want)
+
+
+CASES = [
+    # B, Cin, Cout, H, W, kh, kw, stride, dg, mask, bias
+    (2, 256, 256, 12, 20, 3, 3, 1, 1, False, False),   # FCB 3x3 on P5
+    (2, 256, 256, 12, 20, 3, 5, 1, 1, False, False),   # FCB 3x5
+    (2, 256, 256, 12, 20, 5, 3, 1, 1, False, False),   # FCB 5x3
+    (1, 256, 256, 3, 5, 5, 3, 1, 1, False, False),     # 5x3 on P7 (smaller than the kernel)
+    (2, 256, 256, 6, 10, 3, 3, 1, 4, False, False),    # deform_groups = 4
+    (1, 256, 256, 12, 20, 3, 5, 1, 4, False, False),
+    (2, 128, 128, 24, 40, 3, 3, 2, 1, True, True),     # backbone layer2 block 0 style (stride 2)
+    (2, 128, 128, 12, 20, 3, 3, 1, 1, True, True),
+    (1, 512, 512, 6, 10, 3, 3, 1, 1, True, True),      # backbone layer4
+    (1, 64, 96, 9, 11, 3, 3, 1, 1, True, False),
+    (3, 256, 256, 23, 40, 3, 3, 1, 1, False, False),   # odd height (unpadded 360x640 level)
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
+def test_dcn_vs_oracle(cuda_device, dtype, backend, case):
+    B, Cin, Cout, H, W, kh, kw, s, dg, use_mask, use_bias = case
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    pad = ((kh - 1) // 2, (kw - 1) // 2)
+    Ho, Wo = oracle.out_size(H, kh, s, pad[0], 1), oracle.out_size(W, kw, s, pad[1], 1)
+    x = q(rng.standard_normal((B, Cin, H, W)), dtype)
+    w = q(rng.standard_normal((Cout, Cin, kh, kw)) / np.sqrt(Cin * kh * kw), dtype)
+    off = (rng.standard_normal((B, dg * 2 * kh * kw, Ho, Wo)) * 2.0).astype(np.float32)
+    mask = rng.random((B, dg * kh * kw, Ho, Wo)).astype(np.float32) if use_mask else None
+    bias = rng.standard_normal(Cout).astype(np.float32) if use_bias else None
+    kwargs = dict(stride=s, padding=pad, deform_groups=dg)
+    want = oracle.deform_conv2d(x, off, w, bias, mask, **kwargs)
+    got = run_dcn(cuda_device, dtype, x, off, w, bias, mask, backend=backend, **kwargs)
+    assert rel_err(got, want) <= TOL[dtype], rel_err(got, want)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dcn_layout_and_flag_variants(cuda_device, dtype):
+    """NCHW-contiguous input, bf16 offsets, NHWC offsets, fused ReLU, sigmoid-on-logits: same numbers."""
+    rng = np.random.default_rng(5)
+    B, C, H, W = 2, 64, 10, 12
+    x = q(rng.standard_normal((B, C, H, W)), dtype)
+    w = q(rng.standard_normal((C, C, 3, 3)) / 24.0, dtype)
+    off = q(rng.standard_normal((B, 18, H, W)) * 2.0, torch.bfloat16)      # exactly representable in bf16
+    logits = q(rng.standard_normal((B, 9, H, W)), torch.bfloat16)
+    mask = 1.0 / (1.0 + np.exp(-logits.astype(np.float64)))
+    want = oracle.deform_conv2d(x, off, w, None, mask.astype(np.float32), padding=1)
+    ops = _ops()
+    xd, wd = dev(x, dtype, cuda_device), dev(w, dtype, cuda_device)
+    for off_dtype in (torch.float32, torch.bfloat16):
+        for cl in (False, True):
+            o = dev(off, off_dtype, cuda_device, cl)
+            m = dev(logits, off_dtype, cuda_device, cl)
+            y = ops.deform_conv2d(xd if not cl else xd.contiguous(memory_format=torch.channels_last), o, wd, None, m,
+                                  padding=1, mask_sigmoid=True, relu=True)
+            assert y.shape == (B, C, H, W)
+            assert rel_err(y.float().cpu().numpy(), np.maximum(want, 0)) <= TOL[dtype]
+
+
+def test_dcn_zero_offset_equals_cudnn_conv_full_size(cuda_device):
+    """Size-independent property at the benchmark size: zero offsets, mask 1 == F.conv2d."""
+    ops = _ops()
+    torch.manual_seed(0)
+    for (C, H, W, k, pad) in ((256, 48, 80, (3, 3), (1, 1)), (256, 48, 80, (3, 5), (1, 2)), (256, 24, 40, (5, 3), (2, 1))):
+        x = torch.randn(8, C, H, W, device=cuda_device).contiguous(memory_format=torch.channels_last)
+        w = torch.randn(C, C, *k, device=cuda_device) / (C * k[0] * k[1]) ** 0.5
+        off = torch.zeros(8, 2 * k[0] * k[1], H, W, device=cuda_device)
+        ref = torch.nn.functional.conv2d(x, w, padding=pad)
+        got = ops.deform_conv2d(x, off, w, padding=pad)
+        assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) <= 1e-4
+        gb = ops.deform_conv2d(x.bfloat16(), off, w.bfloat16(), padding=pad)
+        refb = torch.nn.functional.conv2d(x.bfloat16().float(), w.bfloat16().float(), padding=pad)
+        assert rel_err(gb.float().cpu().numpy(), refb.cpu().numpy()) <= 1e-2
+        # plain-conv mode of the same kernel (offset=None)
+        gz = ops.deform_conv2d(x, None, w, padding=pad)
+        assert rel_err(gz.cpu().numpy(), ref.cpu().numpy()) <= 1e-4
+
+
+def test_dcn_linearity_full_size(cuda_device):
+    """y(a*x1 + x2) == a*y(x1) + y(x2) with shared random offsets, P3 at batch 8 (fp32)."""
+    ops = _ops()
+    torch.manual_seed(1)
+    x1 = torch.randn(8, 256, 48, 80, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    x2 = torch.randn_like(x1)
+    w = torch.randn(256, 256, 3, 5, device=cuda_device) / (256 * 15) ** 0.5
+    off = torch.randn(8, 30, 48, 80, device=cuda_device) * 2
+    f = lambda x: ops.deform_conv2d(x, off, w, padding=(1, 2))
+    lhs = f(2.5 * x1 + x2)
+    rhs = 2.5 * f(x1) + f(x2)
+    assert rel_err(lhs.cpu().numpy(), rhs.cpu().numpy()) <= 1e-4
+
+
+def test_dcn_multi_level_launch_matches_single(cuda_device):
+    ops = _ops()
+    torch.manual_seed(2)
+    spec = ops.ConvSpec(256, 256, (3, 5), 1, (1, 2))
+    w = torch.randn(256, 256, 3, 5, device=cuda_device, dtype=torch.bfloat16) / 60
+    wp = ops.pack_weight(w, spec, torch.bfloat16)
+    sizes = [(48, 80), (24, 40), (12, 20), (6, 10), (3, 5)]
+    xs = [torch.randn(2, 256, h, ww, device=cuda_device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last) for h, ww in sizes]
+    offs = [torch.randn(2, 30, h, ww, device=cuda_device) * 2 for h, ww in sizes]
+    multi = ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True)
+    for x, o, ym in zip(xs, offs, multi):
+        y1 = ops.deform_conv2d_multi([x], [o], None, wp, None, spec, relu=True)[0]
+        assert torch.equal(y1, ym)
+        want = np.maximum(oracle.deform_conv2d(x.float().cpu().numpy(), o.cpu().numpy(), w.float().cpu().numpy(), padding=(1, 2)), 0)
+        assert rel_err(ym.float().cpu().numpy(), want) <= 1e-2
+
+
+# ------------------------------------------------------------------------------------------
+# module-level parity with the reference's call sites (golden fixtures)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_backbone_dcn_module_vs_reference(cuda_device, dtype):
+    from stmask_b200.backbone_dcn import make_bottleneck_dcn
+    z = load_golden("backbone_dcn.npz")
+    for name, stride in (("s1", 1), ("s2", 2)):
+        m = make_bottleneck_dcn(16, stride=stride).to(cuda_device)
+        with torch.no_grad():
+            m.weight.copy_(torch.from_numpy(z[f"{name}.weight"]))
+            m.bias.copy_(torch.from_numpy(z[f"{name}.bias"]))
+            m.conv_offset_mask.weight.copy_(torch.from_numpy(z[f"{name}.com_w"]))
+            m.conv_offset_mask.bias.copy_(torch.from_numpy(z[f"{name}.com_b"]))
+        m = m.to(dtype)
+        x = dev(z[f"{name}.dcn_x"], dtype, cuda_device)
+        with torch.no_grad():
+            y = m(x)
+        # bf16: the offset predictor itself runs in bf16, which moves sampling positions; compare
+        # against the fp32 golden with the bf16 tolerance scaled by the offset sensitivity
+        tol = 1e-4 if dtype == torch.float32 else 3e-2
+        assert rel_err(y.float().cpu().numpy(), z[f"{name}.dcn_y"]) <= tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode", ["ada", "ali"])
+def test_feature_align_vs_reference(cuda_device, dtype, mode):
+    from stmask_b200.feature_align import FeatureAlign
+    z = load_golden("feature_align.npz")
+    for name, ks in (("k3x3", (3, 3)), ("k3x5", (3, 5)), ("k5x3", (5, 3)), ("k5x3_p7", (5, 3))):
+        k = f"{mode}.{name}"
+        m = FeatureAlign(32, 41, kernel_size=ks, deformable_groups=1, use_pred_offset=(mode == "ada")).to(cuda_device)
+        with torch.no_grad():
+            m.conv_adaption.weight.copy_(torch.from_numpy(z[f"{k}.w_adaption"]))
+            m.conv.weight.copy_(torch.from_numpy(z[f"{k}.w_conv"]))
+            m.conv.bias.copy_(torch.from_numpy(z[f"{k}.b_conv"]))
+            if mode == "ada":
+                m.conv_offset.weight.copy_(torch.from_numpy(z[f"{k}.w_offset"]))
+        x = dev(z[f"{k}.x"], dtype, cuda_device)
+        shape = dev(z[f"{k}.shape"], torch.float32, cuda_device)
+        if dtype == torch.bfloat16:
+            m.conv_adaption.to(dtype)
+            m.conv.to(dtype)
+        with torch.no_grad():
+            off = m.offsets(shape)
+            dcn = m.calibrate_levels([x], [shape])[0]
+            y = m(x, shape)
+        assert rel_err(off.float().cpu().numpy(), z[f"{k}.offset"]) <= 1e-5, k
+        if dtype == torch.float32:
+            assert rel_err(dcn.cpu().numpy(), z[f"{k}.dcn_relu"]) <= 1e-4, k
+            assert rel_err(y.cpu().numpy(), z[f"{k}.y"]) <= 1e-4, k
+        else:
+            want, _ = oracle.feature_align(q(z[f"{k}.x"], dtype), z[f"{k}.shape"], q(z[f"{k}.w_adaption"], dtype), ks,
+                                           w_offset=z[f"{k}.w_offset"] if mode == "ada" else None)
+            assert rel_err(dcn.float().cpu().numpy(), want) <= 1e-2, k
+
+
+def test_drop_in_modules_match_functional(cuda_device):
+    from dcn_v2 import DCN, DCNv2, dcn_v2_conv
+    from mmcv.ops import DeformConv2d, ModulatedDeformConv2d, ModulatedDeformConv2dPack, deform_conv2d, modulated_deform_conv2d
+    torch.manual_seed(3)
+    x = torch.randn(2, 32, 9, 10, device=cuda_device)
+    off = torch.randn(2, 18, 9, 10, device=cuda_device)
+    mask = torch.rand(2, 9, 9, 10, device=cuda_device)
+    m1 = DeformConv2d(32, 48, (3, 3), padding=(1, 1)).to(cuda_device)
+    want = oracle.deform_conv2d(x.cpu().numpy(), off.cpu().numpy(), m1.weight.detach().cpu().numpy(), padding=1)
+    assert rel_err(m1(x, off).detach().cpu().numpy(), want) <= 1e-4
+    assert rel_err(deform_conv2d(x, off, m1.weight, 1, 1).detach().cpu().numpy(), want) <= 1e-4
+    m2 = ModulatedDeformConv2d(32, 48, 3, padding=1).to(cuda_device)
+    m2.bias.data.normal_()
+    want2 = oracle.deform_conv2d(x.cpu().numpy(), off.cpu().numpy(), m2.weight.detach().cpu().numpy(),
+                                 m2.bias.detach().cpu().numpy(), mask.cpu().numpy(), padding=1)
+    assert rel_err(m2(x, off, mask).detach().cpu().numpy(), want2) <= 1e-4
+    assert rel_err(modulated_deform_conv2d(x, off, mask, m2.weight, m2.bias, 1, 1).detach().cpu().numpy(), want2) <= 1e-4
+    m3 = DCNv2(32, 48, 3, 1, 1).to(cuda_device)
+    m3.load_state_dict(m2.state_dict())
+    assert rel_err(m3(x, off, mask).detach().cpu().numpy(), want2) <= 1e-4
+    assert rel_err(dcn_v2_conv(x, off, mask, m2.weight, m2.bias, 1, 1, 1, 1).detach().cpu().numpy(), want2) <= 1e-4
+    # the *Pack / DCN modules: offsets from their own zero-initialised predictor => plain conv with mask 0.5
+    for cls in (lambda: ModulatedDeformConv2dPack(32, 48, 3, padding=1), lambda: DCN(32, 48, 3, 1, 1)):
+        m4 = cls().to(cuda_device)
+        ref = 0.5 * torch.nn.functional.conv2d(x, m4.weight, None, padding=1) + m4.bias.view(1, -1, 1, 1)
+        assert rel_err(m4(x).detach().cpu().numpy(), ref.detach().cpu().numpy()) <= 1e-4
+    # weight update is picked up (packed-weight cache keyed on the version counter)
+    with torch.no_grad():
+        m1.weight.mul_(2.0)
+    assert rel_err(m1(x, off).detach().cpu().numpy(), 2 * want) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------
+# correlation
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_correlate_golden_reference_call_site(cuda_device, dtype):
+    from stmask_b200.temporal_fusion import correlate, correlate_concat
+    z = load_golden("correlate.npz")
+    for name in ("p11_d1", "p11_d2", "p11_p7", "p5_d1"):
+        P, d = (int(v) for v in z[f"{name}.pd"])
+        x1, x2 = q(z[f"{name}.x1"], dtype), q(z[f"{name}.x2"], dtype)
+        got = correlate(dev(x1, dtype, cuda_device), dev(x2, dtype, cuda_device), P, d)
+        want = z[f"{name}.y"] if dtype == torch.float32 else oracle.correlate(x1, x2, P, d)
+        assert got.shape == want.shape
+        assert rel_err(got.float().cpu().numpy(), want) <= TOL[dtype], name
+    x1, x2 = q(z["p11_d1.x1"], dtype), q(z["p11_d1.x2"], dtype)
+    ta, tb = q(z["concat.t_ref"], dtype), q(z["concat.t_next"], dtype)
+    for cl in (True, False):
+        got = correlate_concat(dev(x1, dtype, cuda_device), dev(x2, dtype, cuda_device), dev(ta, dtype, cuda_device),
+                               dev(tb, dtype, cuda_device), channels_last=cl)
+        want = np.maximum(np.concatenate([oracle.correlate(x1, x2, 11, 1), ta, tb], 1), 0)
+        assert got.shape == want.shape
+        assert rel_err(got.float().cpu().numpy(), want) <= TOL[dtype]
+        if dtype == torch.float32:
+            assert rel_err(got.cpu().numpy(), z["concat.y"]) <= 1e-4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+@pytest.mark.parametrize("shape,P,d", [((2, 256, 24, 40), 11, 1), ((2, 256, 24, 40), 11, 2), ((1, 256, 48, 80), 11, 1),
+                                       ((3, 256, 3, 5), 11, 1), ((2, 256, 6, 10), 11, 2), ((2, 256, 23, 40), 11, 1),
+                                       ((2, 64, 12, 20), 5, 1), ((1, 40, 7, 9), 3, 3), ((1, 13, 6, 7), 7, 1),
+                                       ((1, 512, 12, 20), 11, 1)])
+def test_correlation_vs_oracle(cuda_device, dtype, backend, shape, P, d):
+    from spatial_correlation_sampler import spatial_correlation_sample
+    rng = np.random.default_rng(P * 100 + d + shape[2])
+    x1, x2 = q(rng.standard_normal(shape), dtype), q(rng.standard_normal(shape), dtype)
+    ops = _ops()
+    got = ops.correlation(dev(x1, dtype, cuda_device), dev(x2, dtype, cuda_device), P, d, backend=backend,
+                          out_dtype=torch.float32)
+    want = oracle.correlation(x1, x2, P, d).reshape(shape[0], P * P, shape[2], shape[3])
+    assert rel_err(got.cpu().numpy(), want) <= TOL[dtype]
+    # 5-D drop-in API, NCHW-contiguous inputs
+    got5 = spatial_correlation_sample(dev(x1, dtype, cuda_device), dev(x2, dtype, cuda_device), kernel_size=1, patch_size=P, stride=1,
+                     padding=0, dilation_patch=d)
+    assert got5.shape == (shape[0], P, P, shape[2], shape[3])
+    assert rel_err(got5.float().cpu().numpy().reshape(want.shape), want) <= TOL[dtype]
+
+
+def test_correlation_known_answers_full_size(cuda_device):
+    ops = _ops()
+    torch.manual_seed(4)
+    # shift KAT at the sweep size: x2 = roll(x1, (+2, -1)) => peak at (ph, pw) = (7, 4) in the interior
+    x1 = torch.randn(8, 256, 48, 80, device=cuda_device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x2 = torch.roll(x1, (2, -1), dims=(2, 3))
+    out = ops.correlation(x1, x2, 11, 1, out_dtype=torch.float32)
+    assert (out[:, :, 6:40, 6:70].argmax(1) == 7 * 11 + 4).all()
+    # all ones => C where the displaced pixel is inside the map, 0 outside
+    ones = torch.ones(2, 256, 24, 40, device=cuda_device, dtype=torch.bfloat16)
+    out = ops.correlation(ones, ones, 11, 2, out_dtype=torch.float32).view(2, 11, 11, 24, 40)
+    for ph in (0, 3, 5, 10):
+        for pw in (0, 5, 9):
+            dy, dx = (ph - 5) * 2, (pw - 5) * 2
+            want = torch.zeros(24, 40, device=cuda_device)
+            want[max(0, -dy):24 - max(0, dy), max(0, -dx):40 - max(0, dx)] = 256
+            assert torch.equal(out[0, ph, pw], want)
+    # symmetry: corr(x1, x2)[dy, dx](p) == corr(x2, x1)[-dy, -dx](p + d)
+    a = torch.randn(4, 256, 24, 40, device=cuda_device)
+    b = torch.randn(4, 256, 24, 40, device=cuda_device)
+    ab = ops.correlation(a, b, 11, 1).view(4, 11, 11, 24, 40)
+    ba = ops.correlation(b, a, 11, 1).view(4, 11, 11, 24, 40)
+    assert rel_err(ab[:, 7, 4, 5:15, 8:30].cpu().numpy(), ba[:, 3, 6, 7:17, 7:29].cpu().numpy()) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------
+# error conventions: raise in Python before crossing the C ABI
+# ------------------------------------------------------------------------------------------
+def test_error_conventions(cuda_device):
+    ops = _ops()
+    x = torch.randn(1, 8, 5, 5, device=cuda_device)
+    w = torch.randn(8, 8, 3, 3, device=cuda_device)
+    with pytest.raises(ValueError):
+        ops.deform_conv2d(x, torch.zeros(1, 18, 4, 4, device=cuda_device), w, padding=1)      # wrong offset size
+    with pytest.raises(ValueError):
+        ops.deform_conv2d(x[0], torch.zeros(1, 18, 5, 5, device=cuda_device), w, padding=1)   # not 4-D
+    with pytest.raises(RuntimeError):
+        ops.deform_conv2d(x.cpu(), torch.zeros(1, 18, 5, 5), w.cpu(), padding=1)              # CPU tensors
+    with pytest.raises(TypeError):
+        ops.deform_conv2d(x.half(), torch.zeros(1, 18, 5, 5, device=cuda_device), w.half(), padding=1)
+    with pytest.raises(ValueError):
+        ops.correlation(x, x, patch_size=4)
+    with pytest.raises(ValueError):
+        ops.correlation(x, x[:, :4], patch_size=3)
+    from stmask_b200.compat.spatial_correlation_sampler import spatial_correlation_sample
+    with pytest.raises(NotImplementedError):
+        spatial_correlation_sample(x, x, kernel_size=3, patch_size=3)
+    # batch sizes mmcv's im2col_step would reject (B % 32 != 0 for B > 32) work here
+    xb = torch.randn(36, 8, 5, 5, device=cuda_device)
+    assert ops.deform_conv2d(xb, torch.zeros(36, 18, 5, 5, device=cuda_device), w, padding=1).shape == (36, 8, 5, 5)
+    # empty batch
+    assert ops.deform_conv2d(x[:0], torch.zeros(0, 18, 5, 5, device=cuda_device), w, padding=1).shape == (0, 8, 5, 5)

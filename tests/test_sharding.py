@@ -1,0 +1,93 @@
+"""CPU: clip/frame partitioning and the one-frame halo exchange (world_size 2 over gloo)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from stmask_b200.sharding import exchange_halo, make_plan, temporal_pairs
+
+
+def test_clip_mode_whole_clips_need_no_halo():
+    for g in (1, 2, 4, 8):
+        plan = make_plan(64, 16, g, "clip")
+        assert plan.halos == []
+        assert [plan.local_frames(r) for r in range(g)] == [1024 // g] * g
+        assert sum(plan.local_pairs(r) for r in range(g)) == 64 * 15
+
+
+def test_clip_mode_uneven_split_creates_boundaries():
+    plan = make_plan(3, 5, 2, "clip")          # 15 frames -> 7 + 8; clip 1 is cut between frame 1 and 2
+    assert [plan.local_frames(r) for r in range(2)] == [7, 8]
+    assert [(h.clip, h.frame, h.src, h.dst) for h in plan.halos] == [(1, 2, 0, 1)]
+    assert sum(plan.local_pairs(r) for r in range(2)) == 3 * 4
+
+
+def test_frame_mode_boundaries():
+    plan = make_plan(64, 16, 8, "frame")
+    assert len(plan.halos) == 64 * 7
+    assert all(h.dst == h.src + 1 for h in plan.halos)
+    assert [plan.local_frames(r) for r in range(8)] == [128] * 8
+    assert sum(plan.local_pairs(r) for r in range(8)) == 64 * 15
+    assert len(plan.recv_halos(0)) == 0 and len(plan.recv_halos(3)) == 64 and len(plan.send_halos(7)) == 0
+    with pytest.raises(ValueError):
+        make_plan(1, 1, 1, "bogus")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, mode, n_clips, fpc, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = make_plan(n_clips, fpc, world, mode)
+        C1, C2, H, W = 6, 4, 3, 5
+        # global features: value encodes (clip, frame, channel) so misrouted halos are detectable
+        g = torch.Generator().manual_seed(0)
+        full1 = torch.randn(n_clips, fpc, C1, H, W, generator=g)
+        full2 = torch.randn(n_clips, fpc, C2, H, W, generator=g)
+        loc1 = torch.cat([full1[s.clip, s.start:s.stop] for s in plan.segments[rank]], 0)
+        loc2 = torch.cat([full2[s.clip, s.start:s.stop] for s in plan.segments[rank]], 0)
+        if rank == 1:   # exercise the channels-last message path on one rank's send side too
+            loc1 = loc1.contiguous(memory_format=torch.channels_last)
+            loc2 = loc2.contiguous(memory_format=torch.channels_last)
+        h1, h2 = exchange_halo(plan, rank, [loc1, loc2])
+        ref1, nxt1 = temporal_pairs(plan, rank, loc1, h1)
+        ref2, nxt2 = temporal_pairs(plan, rank, loc2, h2)
+        # expected pairs straight from the global tensors
+        e_ref1, e_nxt1, e_ref2 = [], [], []
+        for s in plan.segments[rank]:
+            for f in range(s.start, s.stop):
+                if f > 0:
+                    e_ref1.append(full1[s.clip, f - 1]); e_nxt1.append(full1[s.clip, f]); e_ref2.append(full2[s.clip, f - 1])
+        ok = (torch.equal(ref1, torch.stack(e_ref1)) and torch.equal(nxt1, torch.stack(e_nxt1))
+              and torch.equal(ref2, torch.stack(e_ref2)) and ref1.shape[0] == plan.local_pairs(rank)
+              and nxt2.shape[0] == plan.local_pairs(rank))
+        q.put((rank, bool(ok), len(plan.recv_halos(rank))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,n_clips,fpc", [("frame", 3, 8), ("clip", 3, 5), ("clip", 4, 4)])
+def test_halo_exchange_world_size_2_gloo(mode, n_clips, fpc):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mode, n_clips, fpc, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    n_halo = {"frame": n_clips, "clip": 1 if (n_clips, fpc) == (3, 5) else 0}[mode]
+    assert res[1][2] == n_halo and res[0][2] == 0
