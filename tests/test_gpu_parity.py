@@ -138,6 +138,7 @@ def test_dcn_zero_offset_equals_cudnn_conv_full_size(cuda_device):
     """Size-independent property at the benchmark size: zero offsets, mask 1 == F.conv2d."""
     ops = _ops()
     torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False          # the cuDNN reference must be real fp32
     for (C, H, W, k, pad) in ((256, 48, 80, (3, 3), (1, 1)), (256, 48, 80, (3, 5), (1, 2)), (256, 24, 40, (5, 3), (2, 1))):
         x = torch.randn(8, C, H, W, device=cuda_device).contiguous(memory_format=torch.channels_last)
         w = torch.randn(C, C, *k, device=cuda_device) / (C * k[0] * k[1]) ** 0.5
