@@ -4,15 +4,15 @@
 //   A[m, (tap, c)] = mask[m, tap] * bilinear(x[b, :, :, c], p(m) + tap + offset[m, tap])
 //
 // A is never written to global memory.  Per CTA (256 or 128 output pixels x one N tile of <= 256):
-//   * warps 0-7  PRODUCERS: once per (tap, deformable group) compute the four bilinear corner
+//   * warps 0-15 PRODUCERS: once per (tap, deformable group) compute the four bilinear corner
 //                weights/offsets of every row (DCN border rule, mask folded in) into shared memory;
 //                then per 64-channel K block gather 4 x 16-byte corner vectors per (row, 8 channels)
 //                (NHWC => contiguous), blend in fp32, round once to bf16 and store into the
 //                128B-swizzled K-major A tile; fence.proxy.async + mbarrier arrive.
 //                After the main loop the same warps run the EPILOGUE: tcgen05.ld the fp32
 //                accumulators, + bias, ReLU, bf16, 16-byte stores to NHWC y.
-//   * warp 8     TMA: the matching [N x 64] slice of the packed OHWI weight -> swizzled B tile.
-//   * warp 9     MMA: one thread issues tcgen05.mma (M=128, N<=256, K=16, bf16 -> fp32 in TMEM),
+//   * warp 16    TMA: the matching [N x 64] slice of the packed OHWI weight -> swizzled B tile.
+//   * warp 17    MMA: one thread issues tcgen05.mma (M=128, N<=256, K=16, bf16 -> fp32 in TMEM),
 //                tcgen05.commit frees the stage; owns the TMEM allocation.
 // Several feature maps that share a weight (FPN levels) are tiles of ONE launch.
 //
@@ -48,7 +48,7 @@ using namespace tc;
 constexpr int BLOCK_K = 64;             // bf16 elements = one 128-byte swizzle row
 constexpr int TILE_M = 128;             // rows per accumulator (UMMA M)
 constexpr int A_TILE_BYTES = TILE_M * 128;
-constexpr int PRODUCER_WARPS = 8;
+constexpr int PRODUCER_WARPS = 16;
 constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;
 constexpr int NUM_THREADS = PRODUCER_THREADS + 64;
 constexpr int MAX_STAGES = 6;
@@ -83,7 +83,8 @@ template <int M_TILES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap tmap_w) {
   constexpr int ROWS = TILE_M * M_TILES;
-  constexpr int PASSES = ROWS / 32;
+  constexpr int ROWS_PER_PASS = PRODUCER_WARPS * 4;     // 64 rows per sweep of the producer warps
+  constexpr int PASSES = ROWS / ROWS_PER_PASS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const SmemLayout<M_TILES> L(a.block_n, a.stages);
@@ -132,7 +133,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   if (warp == PRODUCER_WARPS && lane == 0) {
     prefetch_tensormap(&tmap_w);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], PRODUCER_WARPS + 1);   // 8 producer warps + the TMA thread's expect_tx arrive
+      mbar_init(&full_bar[s], PRODUCER_WARPS + 1);   // producer warps + the TMA thread's expect_tx arrive
       mbar_init(&empty_bar[s], 1);                   // tcgen05.commit
     }
     mbar_init(accum_bar, 1);
@@ -155,109 +156,153 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     // =============================== PRODUCERS ===============================
     const int v = lane & 7;                 // 16-byte (8-channel) slot inside the 64-channel K block
     const int rsub = lane >> 3;             // 4 rows per warp instruction
+    const int row0 = warp * 4 + rsub;       // this thread's row in pass 0; pass j adds j * ROWS_PER_PASS
+    // 128B swizzle: chunk v of row r goes to chunk v ^ (r & 7); r & 7 is the same in every pass
+    const int swz = (v ^ (row0 & 7)) << 4;
     const bool has_off = pr.offset != nullptr, has_mask = pr.mask != nullptr;
     const bool off_bf16 = (p.flags & 0x100) != 0;      // internal flag: offsets/masks stored as bf16
-    int kb = 0, it = 0;
-#pragma unroll 1
-    for (int tap = 0; tap < K; ++tap) {
-      const int ti = tap / p.kw, tj = tap - ti * p.kw;
-#pragma unroll 1
-      for (int g = 0; g < p.dg; ++g, ++it) {
-        const int buf = it & 1;
-        if (tid < ROWS) {
-          const int4 pos = row_pos[tid];
-          Sample4 s;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { s.w[i] = 0.f; s.o[i] = 0; }
-          if (pos.w) {
-            float oy = 0.f, ox = 0.f, mk = 1.f;
-            if (has_off) {
-              const int64_t o = pos.x * pr.off_sn + (int64_t)(g * 2 * K + 2 * tap) * pr.off_sc + pos.y * pr.off_sh + pos.z * pr.off_sw;
-              if (off_bf16) {
-                oy = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.offset)[o]);
-                ox = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.offset)[o + pr.off_sc]);
-              } else {
-                oy = reinterpret_cast<const float*>(pr.offset)[o];
-                ox = reinterpret_cast<const float*>(pr.offset)[o + pr.off_sc];
-              }
-            }
-            if (has_mask) {
-              const int64_t o = pos.x * pr.mask_sn + (int64_t)(g * K + tap) * pr.mask_sc + pos.y * pr.mask_sh + pos.z * pr.mask_sw;
-              mk = off_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.mask)[o])
-                            : reinterpret_cast<const float*>(pr.mask)[o];
-              if (p.flags & STM_DCN_MASK_SIGMOID) mk = sigmoidf_(mk);
-            }
-            const float h = (float)(pos.y * p.sh - p.ph + ti * p.dh) + oy;
-            const float w = (float)(pos.z * p.sw - p.pw + tj * p.dw) + ox;
-            s = make_sample(h, w, pr.in_h, pr.in_w, pr.x_sh, pr.x_sw, mk);
-          }
-          meta_w[buf * ROWS + tid] = make_float4(s.w[0], s.w[1], s.w[2], s.w[3]);
-          meta_o[buf * ROWS + tid] = make_int4(s.o[0], s.o[1], s.o[2], s.o[3]);
-        }
-        named_barrier_sync(1, PRODUCER_THREADS);
-#pragma unroll 1
-        for (int cc = 0; cc < chunks; ++cc, ++kb) {
-          const int s = kb % stages;
-          const uint32_t ring = (uint32_t)(kb / stages);
-          mbar_wait(&empty_bar[s], (ring & 1u) ^ 1u);
-          uint8_t* a_stage = smem + s * L.stage_bytes;
-          const int chan = g * cpd + cc * BLOCK_K + v * 8;
-#pragma unroll
-          for (int p0 = 0; p0 < PASSES; p0 += 4) {
-            uint4 c[4][4];
-            float4 w4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int row = (p0 + j) * 32 + warp * 4 + rsub;
-              w4[j] = meta_w[buf * ROWS + row];
-              const int4 o4 = meta_o[buf * ROWS + row];
-              const __nv_bfloat16* xb = row_x[row] + chan;
-              const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-              c[j][0] = w4[j].x != 0.f ? __ldg(reinterpret_cast<const uint4*>(xb + o4.x)) : z;
-              c[j][1] = w4[j].y != 0.f ? __ldg(reinterpret_cast<const uint4*>(xb + o4.y)) : z;
-              c[j][2] = w4[j].z != 0.f ? __ldg(reinterpret_cast<const uint4*>(xb + o4.z)) : z;
-              c[j][3] = w4[j].w != 0.f ? __ldg(reinterpret_cast<const uint4*>(xb + o4.w)) : z;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int row = (p0 + j) * 32 + warp * 4 + rsub;
-              const uint32_t* q0 = reinterpret_cast<const uint32_t*>(&c[j][0]);
-              const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&c[j][1]);
-              const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&c[j][2]);
-              const uint32_t* q3 = reinterpret_cast<const uint32_t*>(&c[j][3]);
-              uint32_t o[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float lo = w4[j].x * bf16_lo(q0[i]);
-                float hi = w4[j].x * bf16_hi(q0[i]);
-                lo = fmaf(w4[j].y, bf16_lo(q1[i]), lo);
-                hi = fmaf(w4[j].y, bf16_hi(q1[i]), hi);
-                lo = fmaf(w4[j].z, bf16_lo(q2[i]), lo);
-                hi = fmaf(w4[j].z, bf16_hi(q2[i]), hi);
-                lo = fmaf(w4[j].w, bf16_lo(q3[i]), lo);
-                hi = fmaf(w4[j].w, bf16_hi(q3[i]), hi);
-                o[i] = pack_bf16(lo, hi);
-              }
-              const int mt = row / TILE_M, rl = row % TILE_M;
-              uint8_t* dst = a_stage + mt * A_TILE_BYTES + rl * 128 + ((v ^ (rl & 7)) << 4);
-              *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full_bar[s]);
+    const int4 pos = (tid < ROWS) ? row_pos[tid] : make_int4(0, 0, 0, 0);
+    const int n_iter = K * p.dg;
+
+    // raw (dy, dx, mask) of this thread's row for iteration `it`; issued one iteration ahead so the
+    // global-load latency hides behind the gather instead of stalling everybody at the named barrier
+    auto load_raw = [&](int it_, float& oy, float& ox, float& mk) {
+      oy = 0.f; ox = 0.f; mk = 1.f;
+      if (tid >= ROWS || !pos.w || it_ >= n_iter) return;
+      const int tap_ = it_ / p.dg, g_ = it_ - tap_ * p.dg;
+      if (has_off) {
+        const int64_t o = pos.x * pr.off_sn + (int64_t)(g_ * 2 * K + 2 * tap_) * pr.off_sc + pos.y * pr.off_sh + pos.z * pr.off_sw;
+        if (off_bf16) {
+          oy = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.offset)[o]);
+          ox = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.offset)[o + pr.off_sc]);
+        } else {
+          oy = reinterpret_cast<const float*>(pr.offset)[o];
+          ox = reinterpret_cast<const float*>(pr.offset)[o + pr.off_sc];
         }
       }
+      if (has_mask) {
+        const int64_t o = pos.x * pr.mask_sn + (int64_t)(g_ * K + tap_) * pr.mask_sc + pos.y * pr.mask_sh + pos.z * pr.mask_sw;
+        mk = off_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.mask)[o])
+                      : reinterpret_cast<const float*>(pr.mask)[o];
+      }
+    };
+
+    // One gather task = (row, 8 channels) of one K block: 4 corner loads, fp32 blend, one 16-byte store.
+    // Two register sets (A, B) rotate so the loads of task t+1 are in flight while task t is blended.
+    struct GTask {
+      float4 w;
+      uint8_t* dst;
+      uint4 c[4];
+    };
+    auto issue = [&](GTask& t, int buf, int row, int chan, uint8_t* a_stage) {
+      t.w = meta_w[buf * ROWS + row];
+      const int4 o4 = meta_o[buf * ROWS + row];
+      const __nv_bfloat16* xb = row_x[row] + chan;
+      t.dst = a_stage + row * 128 + swz;                 // row r of the (stacked) A tiles lives at r * 128
+      const uint4* s0 = reinterpret_cast<const uint4*>(xb + o4.x);
+      const uint4* s1 = reinterpret_cast<const uint4*>(xb + o4.y);
+      const uint4* s2 = reinterpret_cast<const uint4*>(xb + o4.z);
+      const uint4* s3 = reinterpret_cast<const uint4*>(xb + o4.w);
+      // every lane's four corners inside the map (the common, interior case): plain loads.  Otherwise
+      // zero-weight corners are NOT read, so data outside the sample can never leak in (0 * Inf).
+      if (__all_sync(0xffffffffu, (t.w.x * t.w.y) * (t.w.z * t.w.w) != 0.f)) {
+        t.c[0] = __ldg(s0); t.c[1] = __ldg(s1); t.c[2] = __ldg(s2); t.c[3] = __ldg(s3);
+      } else {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        t.c[0] = t.w.x != 0.f ? __ldg(s0) : z;
+        t.c[1] = t.w.y != 0.f ? __ldg(s1) : z;
+        t.c[2] = t.w.z != 0.f ? __ldg(s2) : z;
+        t.c[3] = t.w.w != 0.f ? __ldg(s3) : z;
+      }
+    };
+    auto finish = [&](const GTask& t) {
+      const uint32_t* q0 = reinterpret_cast<const uint32_t*>(&t.c[0]);
+      const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&t.c[1]);
+      const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&t.c[2]);
+      const uint32_t* q3 = reinterpret_cast<const uint32_t*>(&t.c[3]);
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float lo = t.w.x * bf16_lo(q0[i]);
+        float hi = t.w.x * bf16_hi(q0[i]);
+        lo = fmaf(t.w.y, bf16_lo(q1[i]), lo);
+        hi = fmaf(t.w.y, bf16_hi(q1[i]), hi);
+        lo = fmaf(t.w.z, bf16_lo(q2[i]), lo);
+        hi = fmaf(t.w.z, bf16_hi(q2[i]), hi);
+        lo = fmaf(t.w.w, bf16_lo(q3[i]), lo);
+        hi = fmaf(t.w.w, bf16_hi(q3[i]), hi);
+        o[i] = pack_bf16(lo, hi);
+      }
+      *reinterpret_cast<uint4*>(t.dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    };
+    auto publish = [&](int stage) {        // this warp's part of the A tile of `stage` is complete
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    };
+
+    GTask A, B;
+    int stage = 0, prev_stage = 0;
+    uint32_t phase = 0;
+    bool pending = false;                   // B holds the last task of the previous K block
+    float r_oy, r_ox, r_mk;
+    load_raw(0, r_oy, r_ox, r_mk);
+#pragma unroll 1
+    for (int it = 0; it < n_iter; ++it) {
+      const int tap = it / p.dg, g = it - tap * p.dg;
+      const int ti = tap / p.kw, tj = tap - ti * p.kw;
+      const int buf = it & 1;
+      if (tid < ROWS) {
+        Sample4 sm;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { sm.w[i] = 0.f; sm.o[i] = 0; }
+        if (pos.w) {
+          const float mk = (has_mask && (p.flags & STM_DCN_MASK_SIGMOID)) ? sigmoidf_(r_mk) : r_mk;
+          const float h = (float)(pos.y * p.sh - p.ph + ti * p.dh) + r_oy;
+          const float w = (float)(pos.z * p.sw - p.pw + tj * p.dw) + r_ox;
+          sm = make_sample(h, w, pr.in_h, pr.in_w, pr.x_sh, pr.x_sw, mk);
+        }
+        meta_w[buf * ROWS + tid] = make_float4(sm.w[0], sm.w[1], sm.w[2], sm.w[3]);
+        meta_o[buf * ROWS + tid] = make_int4(sm.o[0], sm.o[1], sm.o[2], sm.o[3]);
+      }
+      load_raw(it + 1, r_oy, r_ox, r_mk);
+      // meta[buf] was last read two iterations ago; every thread has passed the previous barrier since
+      named_barrier_sync(1, PRODUCER_THREADS);
+#pragma unroll 1
+      for (int cc = 0; cc < chunks; ++cc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* a_stage = smem + stage * L.stage_bytes;
+        const int chan = g * cpd + cc * BLOCK_K + v * 8;
+#pragma unroll
+        for (int j = 0; j < PASSES; j += 2) {
+          issue(A, buf, row0 + j * ROWS_PER_PASS, chan, a_stage);
+          if (j == 0) {
+            if (pending) { finish(B); publish(prev_stage); }
+          } else {
+            finish(B);
+          }
+          issue(B, buf, row0 + (j + 1) * ROWS_PER_PASS, chan, a_stage);
+          finish(A);
+        }
+        pending = true;
+        prev_stage = stage;
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
     }
+    if (pending) { finish(B); publish(prev_stage); }
     // =============================== EPILOGUE ===============================
     mbar_wait(accum_bar, 0);
     tcgen05_fence_after();
+    // warp w may only touch TMEM lanes [32 (w % 4), +32).  The four warp groups (w / 4) split the
+    // accumulators: M_TILES == 2 -> (tile, column half); M_TILES == 1 -> column quarter.
     const int q = warp & 3;
-    const int mt = (M_TILES == 2) ? (warp >> 2) : 0;
-    // M_TILES == 1: warps w and w+4 own the same TMEM lanes and split the 16-column chunks between them
-    const int half = ((block_n / 16 + 1) / 2) * 16;
-    const int c_begin = (M_TILES == 2 || warp < 4) ? 0 : half;
-    const int c_end = (M_TILES == 2 || warp >= 4) ? block_n : half;
+    const int grp = warp >> 2;
+    const int mt = (M_TILES == 2) ? (grp & 1) : 0;
+    const int part = (M_TILES == 2) ? (grp >> 1) : grp;
+    constexpr int PARTS = (M_TILES == 2) ? 2 : 4;
+    const int nchunk = block_n / 16;
+    const int c_begin = (part * nchunk / PARTS) * 16;
+    const int c_end = ((part + 1) * nchunk / PARTS) * 16;
     const int row = mt * TILE_M + q * 32 + lane;
     const int64_t yoff = row_y[row];
     __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(pr.y) + (yoff >= 0 ? yoff : 0) + n0;
@@ -287,19 +332,19 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   } else if (warp == PRODUCER_WARPS) {
     // =============================== TMA (weights) ===============================
     if (lane == 0) {
-      int kb = 0;
+      int s = 0;
+      uint32_t phase = 0;
 #pragma unroll 1
       for (int tap = 0; tap < K; ++tap)
 #pragma unroll 1
         for (int g = 0; g < p.dg; ++g)
 #pragma unroll 1
-          for (int cc = 0; cc < chunks; ++cc, ++kb) {
-            const int s = kb % stages;
-            const uint32_t ring = (uint32_t)(kb / stages);
-            mbar_wait(&empty_bar[s], (ring & 1u) ^ 1u);
+          for (int cc = 0; cc < chunks; ++cc) {
+            mbar_wait_relaxed(&empty_bar[s], phase ^ 1u);
             mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(block_n * 128));
             tma_load_2d(smem + s * L.stage_bytes + M_TILES * A_TILE_BYTES, &tmap_w, &full_bar[s],
                         tap * p.in_c + g * cpd + cc * BLOCK_K, n0);
+            if (++s == stages) { s = 0; phase ^= 1u; }
           }
     }
   } else {
@@ -307,11 +352,11 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(TILE_M, (uint32_t)block_n);
       const int num_kb = K * p.dg * chunks;
+      int s = 0;
+      uint32_t phase = 0;
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ring = (uint32_t)(kb / stages);
-        mbar_wait(&full_bar[s], ring & 1u);
+        mbar_wait_relaxed(&full_bar[s], phase);
         tcgen05_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * L.stage_bytes);
         const uint64_t bdesc = umma_desc_sw128(a_addr + M_TILES * A_TILE_BYTES);
@@ -324,6 +369,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
                       (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);          // stage reusable once these MMAs have read it
+        if (++s == stages) { s = 0; phase ^= 1u; }
       }
       umma_commit(accum_bar);                // accumulators complete
     }

@@ -1,0 +1,84 @@
+"""Run ONE hot-path operator a few times (for ncu captures and quick timing).
+    python tools/profile_case.py fcb35|fcb33|fcb53|bb128s2|bb128|bb256|bb512s2|corr|corrsweep [--frames 72] [--reps 5] [--backend auto]
+"""
+import argparse
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from stmask_b200 import ops  # noqa: E402
+from stmask_b200.hotpath import fpn_level_sizes  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("case")
+ap.add_argument("--frames", type=int, default=72)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--backend", default="auto")
+a = ap.parse_args()
+dev = "cuda"
+torch.manual_seed(0)
+F = a.frames
+
+
+def timeit(fn, flops=None, nbytes=None):
+    fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.reps)]
+    for s, e in evs:
+        s.record(); fn(); e.record()
+    torch.cuda.synchronize()
+    ms = [s.elapsed_time(e) for s, e in evs]
+    m = statistics.median(ms)
+    msg = f"{a.case}: median {m:.4f} ms (min {min(ms):.4f})"
+    if flops:
+        msg += f"  {flops / m / 1e9:.1f} TFLOP/s"
+    if nbytes:
+        msg += f"  {nbytes / m / 1e6:.1f} GB/s"
+    print(msg)
+
+
+if a.case.startswith("fcb"):
+    kh, kw = {"fcb33": (3, 3), "fcb35": (3, 5), "fcb53": (5, 3)}[a.case]
+    spec = ops.ConvSpec(256, 256, (kh, kw), 1, ((kh - 1) // 2, (kw - 1) // 2))
+    w = (torch.randn(256, 256, kh, kw, device=dev) / (256 * kh * kw) ** 0.5).bfloat16()
+    wp = ops.pack_weight(w, spec, torch.bfloat16)
+    lv = fpn_level_sizes()
+    xs = [torch.randn(F, 256, h, ww, device=dev).bfloat16().contiguous(memory_format=torch.channels_last) for h, ww in lv]
+    offs = [torch.randn(F, 2 * kh * kw, h, ww, device=dev) * 2 for h, ww in lv]
+    outs = ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=a.backend)
+    px = sum(h * ww for h, ww in lv)
+    timeit(lambda: ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=a.backend, outs=outs),
+           flops=2.0 * F * px * 256 * 256 * kh * kw)
+elif a.case.startswith("bb"):
+    C, H, W, s = {"bb128s2": (128, 96, 160, 2), "bb128": (128, 48, 80, 1), "bb256s2": (256, 48, 80, 2), "bb256": (256, 24, 40, 1),
+                  "bb512s2": (512, 24, 40, 2)}[a.case]
+    spec = ops.ConvSpec(C, C, 3, s, 1)
+    Ho, Wo = spec.out_hw(H, W)
+    w = (torch.randn(C, C, 3, 3, device=dev) / (C * 9) ** 0.5).bfloat16()
+    wp = ops.pack_weight(w, spec, torch.bfloat16)
+    x = torch.randn(F, C, H, W, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    om = torch.randn(F, 27, Ho, Wo, device=dev).bfloat16()
+    bias = torch.randn(C, device=dev)
+    outs = ops.deform_conv2d_multi([x], [om[:, :18]], [om[:, 18:]], wp, bias, spec, mask_sigmoid=True, backend=a.backend)
+    timeit(lambda: ops.deform_conv2d_multi([x], [om[:, :18]], [om[:, 18:]], wp, bias, spec, mask_sigmoid=True, backend=a.backend, outs=outs),
+           flops=2.0 * F * Ho * Wo * C * C * 9)
+elif a.case == "corr":
+    n = F - 1
+    x1 = torch.randn(n, 256, 24, 40, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    x2 = torch.randn_like(x1)
+    t1, t2 = torch.randn_like(x1), torch.randn_like(x1)
+    fn = lambda: ops.correlation(x1, x2, 11, 1, scale=1 / 256, relu=True, feats=(t1, t2), channels_last=True, backend=a.backend)
+    timeit(fn, nbytes=n * 960 * (633 + 2 * 256 + 2 * 256) * 2.0)
+elif a.case == "corrsweep":       # BASELINE.json configs[1]: batch 8 over P3..P7, plain cost volume
+    lv = fpn_level_sizes()
+    xs = [(torch.randn(8, 256, h, ww, device=dev).bfloat16().contiguous(memory_format=torch.channels_last),
+           torch.randn(8, 256, h, ww, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)) for h, ww in lv]
+    px = sum(h * ww for h, ww in lv)
+    fn = lambda: [ops.correlation(p, q, 11, 1, backend=a.backend) for p, q in xs]
+    timeit(fn, nbytes=8 * px * (2 * 256 + 121) * 2.0)
+else:
+    raise SystemExit("unknown case")
