@@ -32,8 +32,16 @@ def timeit(fn, flops=None, nbytes=None):
         s.record(); fn(); e.record()
     torch.cuda.synchronize()
     ms = [s.elapsed_time(e) for s, e in evs]
-    m = statistics.median(ms)
-    msg = f"{a.case}: median {m:.4f} ms (min {min(ms):.4f})"
+    # back-to-back launches between ONE pair of events: launch latency is hidden by the queue
+    s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nb = max(10, a.reps * 4)
+    s0.record()
+    for _ in range(nb):
+        fn()
+    e0.record()
+    torch.cuda.synchronize()
+    m = min(statistics.median(ms), s0.elapsed_time(e0) / nb)
+    msg = f"{a.case}: {m:.4f} ms (single-launch median {statistics.median(ms):.4f}, back-to-back {s0.elapsed_time(e0) / nb:.4f})"
     if flops:
         msg += f"  {flops / m / 1e9:.1f} TFLOP/s"
     if nbytes:
