@@ -232,8 +232,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    full_plan = plan if world > 1 else sharding.make_plan(args.clips_per_gpu, args.frames_per_clip, 1, "clip")
+
     def step(x):
-        return hp(x, plan if world > 1 else None, rank)
+        o = hp(x, full_plan, rank)
+        if isinstance(o.get("tf.concat"), list):        # one tensor per whole clip
+            for i, t_ in enumerate(o.pop("tf.concat")):
+                o[f"tf.concat{i}"] = t_
+        return o
 
     for _ in range(args.warmup):
         out = step(inp)

@@ -156,10 +156,18 @@ class HotPath(torch.nn.Module):
             n = inp["tf.fpn"].shape[0]
             if plan is None:
                 plan = sharding.make_plan(1, n, 1, "clip")
-            fpn_ref, fpn_next = sharding.temporal_pairs(plan, rank, inp["tf.fpn"], halo[0] if halo else None)
-            t2s_ref, t2s_next = sharding.temporal_pairs(plan, rank, inp["tf.t2s"], halo[1] if halo else None)
-            if fpn_next.shape[0] > 0:
-                out["tf.concat"] = self.temporal_fusion(fpn_ref, fpn_next, t2s_ref, t2s_next)
+            slices = sharding.pair_slices(plan, rank)
+            if slices is not None and len(slices) <= 4:
+                # whole clips on this rank: (frames[a:b-1], frames[a+1:b]) are views, one launch per clip
+                fpn, t2s = inp["tf.fpn"], inp["tf.t2s"]
+                outs = [self.temporal_fusion(fpn[a:b - 1], fpn[a + 1:b], t2s[a:b - 1], t2s[a + 1:b]) for a, b in slices]
+                if outs:
+                    out["tf.concat"] = outs[0] if len(outs) == 1 else outs
+            else:
+                fpn_ref, fpn_next = sharding.temporal_pairs(plan, rank, inp["tf.fpn"], halo[0] if halo else None)
+                t2s_ref, t2s_next = sharding.temporal_pairs(plan, rank, inp["tf.t2s"], halo[1] if halo else None)
+                if fpn_next.shape[0] > 0:
+                    out["tf.concat"] = self.temporal_fusion(fpn_ref, fpn_next, t2s_ref, t2s_next)
         return out
 
     def temporal_fusion(self, fpn_ref, fpn_next, t2s_ref, t2s_next):

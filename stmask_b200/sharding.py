@@ -174,7 +174,21 @@ def temporal_pairs(plan: ShardPlan, rank: int, feat: torch.Tensor, halo: Optiona
     """(ref, next) batches for the correlation of this rank: next = every local frame that is not a
     clip start; ref = the frame before it — local, or the received halo at a shard boundary.
     Mirrors the train-time batched call (STMask.py:289-297: ref = frames[::2], next = frames[1::2])
-    generalised to clips of any length."""
+    generalised to clips of any length.  The gather runs on the NHWC view, so channels-last
+    features stay channels-last (no re-layout before the correlation kernel)."""
+    ref_idx, next_idx = pair_indices(plan, rank)
+    src = feat if halo is None else torch.cat([feat, halo.to(feat.dtype)], 0)
+    dev = feat.device
+    ri = torch.as_tensor(ref_idx, device=dev, dtype=torch.long)
+    ni = torch.as_tensor(next_idx, device=dev, dtype=torch.long)
+    if feat.dim() == 4 and feat.stride(1) == 1:
+        return (src.permute(0, 2, 3, 1).index_select(0, ri).permute(0, 3, 1, 2),
+                feat.permute(0, 2, 3, 1).index_select(0, ni).permute(0, 3, 1, 2))
+    return src.index_select(0, ri), feat.index_select(0, ni)
+
+
+def pair_indices(plan: ShardPlan, rank: int) -> Tuple[List[int], List[int]]:
+    """Row indices (into [local frames ++ received halos]) of the reference and the next frame of every pair."""
     recvs = plan.recv_halos(rank)
     halo_row = {(h.clip, h.frame): i for i, h in enumerate(recvs)}
     ref_idx, next_idx = [], []
@@ -186,7 +200,13 @@ def temporal_pairs(plan: ShardPlan, rank: int, feat: torch.Tensor, halo: Optiona
             loc = s.offset + (f - s.start)
             next_idx.append(loc)
             ref_idx.append(loc - 1 if f > s.start else n_local + halo_row[(s.clip, f)])
-    src = feat if halo is None else torch.cat([feat, halo.to(feat.dtype)], 0)
-    dev = feat.device
-    return (src.index_select(0, torch.as_tensor(ref_idx, device=dev, dtype=torch.long)),
-            feat.index_select(0, torch.as_tensor(next_idx, device=dev, dtype=torch.long)))
+    return ref_idx, next_idx
+
+
+def pair_slices(plan: ShardPlan, rank: int) -> Optional[List[Tuple[int, int]]]:
+    """When no pair of this rank crosses a shard boundary, the pairs of a segment are simply
+    (frames[a:b-1], frames[a+1:b]): return the [a, b) ranges so the caller can use VIEWS (zero copies).
+    Returns None when a halo is involved."""
+    if plan.recv_halos(rank):
+        return None
+    return [(s.offset, s.offset + s.length) for s in plan.segments[rank] if s.length > 1]
