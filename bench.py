@@ -150,7 +150,7 @@ def cpu_baseline(hp_cfg, budget_s=20.0):
                       f"{dt:.1f} s of CPU work"}
 
 
-def run_reference(args, hp_cfg):
+def run_reference(args, hp_cfg, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -165,7 +165,7 @@ def run_reference(args, hp_cfg):
     v = steps / dt
     cores = os.cpu_count() or 1
     sample = "each step = 1 frame (+1 TF pair) of the hot path on the host cores, fp32: torchvision.ops.deform_conv2d CPU + oracle C correlation (OpenMP)"
-    print(json.dumps({
+    print(file=real_stdout, flush=True, *[json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/sec", "n_gpus": args.gpus, "steps": steps,
         "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -173,11 +173,21 @@ def run_reference(args, hp_cfg):
         "cpu_baseline": {"value": v, "unit": "frames/sec", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })])
 
 
 # ----------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner) may write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the run and keep the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -200,7 +210,7 @@ def main():
     hp_cfg = HotPathConfig(backbone=args.backbone, fcb=None if args.fcb == "none" else args.fcb,
                            dtype=torch.bfloat16 if args.dtype == "bf16" else torch.float32, backend=args.backend)
     if args.impl == "reference":
-        run_reference(args, hp_cfg)
+        run_reference(args, hp_cfg, real_stdout)
         return
 
     import torch.distributed as dist
@@ -362,7 +372,7 @@ def main():
             "roofline": roof, "roofline_correlation": corr_roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks.summary(),
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

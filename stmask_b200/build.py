@@ -22,7 +22,7 @@ LIB = os.path.join(LIBDIR, "libstmask_b200.so")
 SOURCES = ["abi.cu", "dcn_simt.cu", "dcn_tc.cu", "corr_simt.cu", "corr_tc.cu", "layout.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-              "-Xptxas", "-v"]
+              "-Xptxas", "-v"] + (["-DSTM_DCN_EXPERIMENTS"] if os.environ.get("STM_DCN_EXPERIMENTS") else [])
 
 
 def _nvcc() -> str:

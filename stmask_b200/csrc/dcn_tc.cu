@@ -7,7 +7,8 @@
 //   * warps 0-15 PRODUCERS: once per (tap, deformable group) compute the four bilinear corner
 //                weights/offsets of every row (DCN border rule, mask folded in) into shared memory;
 //                then per 64-channel K block gather 4 x 16-byte corner vectors per (row, 8 channels)
-//                (NHWC => contiguous), blend in fp32, round once to bf16 and store into the
+//                (NHWC => contiguous), blend with fp32 accumulation (FHFMA.BF16: bf16 corner weights, no
+//                unpack instructions), round once to bf16 and store into the
 //                128B-swizzled K-major A tile; fence.proxy.async + mbarrier arrive.
 //                After the main loop the same warps run the EPILOGUE: tcgen05.ld the fp32
 //                accumulators, + bias, ReLU, bf16, 16-byte stores to NHWC y.
@@ -79,7 +80,7 @@ struct SmemLayout {
   }
 };
 
-template <int M_TILES>
+template <int M_TILES, int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap tmap_w) {
   constexpr int ROWS = TILE_M * M_TILES;
@@ -88,7 +89,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const SmemLayout<M_TILES> L(a.block_n, a.stages);
-  float4* meta_w = reinterpret_cast<float4*>(smem + L.meta_w);
+  uint4* meta_w = reinterpret_cast<uint4*>(smem + L.meta_w);    // {w0|w1, w2|w3 as bf16 pairs, nonzero-corner bits, -}
   int4* meta_o = reinterpret_cast<int4*>(smem + L.meta_o);
   const __nv_bfloat16** row_x = reinterpret_cast<const __nv_bfloat16**>(smem + L.row_x);
   int64_t* row_y = reinterpret_cast<int64_t*>(smem + L.row_y);
@@ -190,29 +191,32 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     // One gather task = (row, 8 channels) of one K block: 4 corner loads, fp32 blend, one 16-byte store.
     // Two register sets (A, B) rotate so the loads of task t+1 are in flight while task t is blended.
     struct GTask {
-      float4 w;
-      uint8_t* dst;
+      uint32_t w01, w23;   // bf16 corner weights (w0 | w1 << 16, w2 | w3 << 16)
+      uint32_t dst;        // shared-memory address of this task's 16-byte slot in the A tile
       uint4 c[4];
     };
-    auto issue = [&](GTask& t, int buf, int row, int chan, uint8_t* a_stage) {
-      t.w = meta_w[buf * ROWS + row];
+    auto issue = [&](GTask& t, int buf, int row, int chan, uint32_t a_stage) {
+      const uint4 mw = meta_w[buf * ROWS + row];
       const int4 o4 = meta_o[buf * ROWS + row];
       const __nv_bfloat16* xb = row_x[row] + chan;
+      t.w01 = mw.x; t.w23 = mw.y;
       t.dst = a_stage + row * 128 + swz;                 // row r of the (stacked) A tiles lives at r * 128
       const uint4* s0 = reinterpret_cast<const uint4*>(xb + o4.x);
       const uint4* s1 = reinterpret_cast<const uint4*>(xb + o4.y);
       const uint4* s2 = reinterpret_cast<const uint4*>(xb + o4.z);
       const uint4* s3 = reinterpret_cast<const uint4*>(xb + o4.w);
-      // every lane's four corners inside the map (the common, interior case): plain loads.  Otherwise
+      // every lane's four corners carry weight (the common, interior case): plain loads.  Otherwise
       // zero-weight corners are NOT read, so data outside the sample can never leak in (0 * Inf).
-      if (__all_sync(0xffffffffu, (t.w.x * t.w.y) * (t.w.z * t.w.w) != 0.f)) {
+      if (DBG == 1) {
+        t.c[0] = t.c[1] = t.c[2] = t.c[3] = make_uint4((uint32_t)(uintptr_t)s0, (uint32_t)(uintptr_t)s1, (uint32_t)(uintptr_t)s2, (uint32_t)(uintptr_t)s3);
+      } else if (__all_sync(0xffffffffu, mw.z == 15u)) {
         t.c[0] = __ldg(s0); t.c[1] = __ldg(s1); t.c[2] = __ldg(s2); t.c[3] = __ldg(s3);
       } else {
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        t.c[0] = t.w.x != 0.f ? __ldg(s0) : z;
-        t.c[1] = t.w.y != 0.f ? __ldg(s1) : z;
-        t.c[2] = t.w.z != 0.f ? __ldg(s2) : z;
-        t.c[3] = t.w.w != 0.f ? __ldg(s3) : z;
+        t.c[0] = (mw.z & 1u) ? __ldg(s0) : z;
+        t.c[1] = (mw.z & 2u) ? __ldg(s1) : z;
+        t.c[2] = (mw.z & 4u) ? __ldg(s2) : z;
+        t.c[3] = (mw.z & 8u) ? __ldg(s3) : z;
       }
     };
     auto finish = [&](const GTask& t) {
@@ -220,20 +224,29 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&t.c[1]);
       const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&t.c[2]);
       const uint32_t* q3 = reinterpret_cast<const uint32_t*>(&t.c[3]);
+      uint16_t w0, w1, w2, w3;
+      split16(t.w01, w0, w1);
+      split16(t.w23, w2, w3);
       uint32_t o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float lo = t.w.x * bf16_lo(q0[i]);
-        float hi = t.w.x * bf16_hi(q0[i]);
-        lo = fmaf(t.w.y, bf16_lo(q1[i]), lo);
-        hi = fmaf(t.w.y, bf16_hi(q1[i]), hi);
-        lo = fmaf(t.w.z, bf16_lo(q2[i]), lo);
-        hi = fmaf(t.w.z, bf16_hi(q2[i]), hi);
-        lo = fmaf(t.w.w, bf16_lo(q3[i]), lo);
-        hi = fmaf(t.w.w, bf16_hi(q3[i]), hi);
+        uint16_t a0, a1, b0, b1, c0, c1, d0, d1;
+        split16(q0[i], a0, a1);
+        split16(q1[i], b0, b1);
+        split16(q2[i], c0, c1);
+        split16(q3[i], d0, d1);
+        float lo = fma_bf16(a0, w0, 0.f);
+        float hi = fma_bf16(a1, w0, 0.f);
+        lo = fma_bf16(b0, w1, lo);
+        hi = fma_bf16(b1, w1, hi);
+        lo = fma_bf16(c0, w2, lo);
+        hi = fma_bf16(c1, w2, hi);
+        lo = fma_bf16(d0, w3, lo);
+        hi = fma_bf16(d1, w3, hi);
         o[i] = pack_bf16(lo, hi);
       }
-      *reinterpret_cast<uint4*>(t.dst) = make_uint4(o[0], o[1], o[2], o[3]);
+      if (DBG == 3) { o[0] = q0[0]; o[1] = q0[1]; o[2] = q0[2]; o[3] = q0[3]; }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t.dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
     };
     auto publish = [&](int stage) {        // this warp's part of the A tile of `stage` is complete
       fence_proxy_async_smem();
@@ -262,7 +275,12 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
           const float w = (float)(pos.z * p.sw - p.pw + tj * p.dw) + r_ox;
           sm = make_sample(h, w, pr.in_h, pr.in_w, pr.x_sh, pr.x_sw, mk);
         }
-        meta_w[buf * ROWS + tid] = make_float4(sm.w[0], sm.w[1], sm.w[2], sm.w[3]);
+        {
+          const uint32_t w01 = pack_bf16(sm.w[0], sm.w[1]), w23 = pack_bf16(sm.w[2], sm.w[3]);
+          const uint32_t nz = ((w01 & 0x7fffu) ? 1u : 0u) | ((w01 & 0x7fff0000u) ? 2u : 0u) | ((w23 & 0x7fffu) ? 4u : 0u) |
+                              ((w23 & 0x7fff0000u) ? 8u : 0u);
+          meta_w[buf * ROWS + tid] = make_uint4(w01, w23, nz, 0u);
+        }
         meta_o[buf * ROWS + tid] = make_int4(sm.o[0], sm.o[1], sm.o[2], sm.o[3]);
       }
       load_raw(it + 1, r_oy, r_ox, r_mk);
@@ -271,7 +289,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
 #pragma unroll 1
       for (int cc = 0; cc < chunks; ++cc) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        uint8_t* a_stage = smem + stage * L.stage_bytes;
+        const uint32_t a_stage = smem_u32(smem + stage * L.stage_bytes);
         const int chan = g * cpd + cc * BLOCK_K + v * 8;
 #pragma unroll
         for (int j = 0; j < PASSES; j += 2) {
@@ -365,7 +383,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
           const uint64_t adesc = umma_desc_sw128(a_addr + mt * A_TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_bf16(tmem_base + (uint32_t)(mt * block_n), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+            if (DBG != 2) umma_bf16(tmem_base + (uint32_t)(mt * block_n), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                       (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);          // stage reusable once these MMAs have read it
@@ -405,14 +423,14 @@ int sm_count() {
   return n;
 }
 
-template <int M_TILES>
+template <int M_TILES, int DBG = 0>
 int launch_t(const TcArgs& args, const CUtensorMap& tmap, dim3 grid, int smem_bytes, cudaStream_t stream) {
   static int configured = 0;
   if (configured < smem_bytes) {
-    STM_CUDA_OK(cudaFuncSetAttribute(dcn_tc_kernel<M_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    STM_CUDA_OK(cudaFuncSetAttribute(dcn_tc_kernel<M_TILES, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = smem_bytes;
   }
-  dcn_tc_kernel<M_TILES><<<grid, NUM_THREADS, smem_bytes, stream>>>(args, tmap);
+  dcn_tc_kernel<M_TILES, DBG><<<grid, NUM_THREADS, smem_bytes, stream>>>(args, tmap);
   count_launch();
   STM_CUDA_OK(cudaGetLastError());
   return STM_OK;
@@ -502,6 +520,14 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return STM_ERR_CUDA; }
 
   const dim3 grid((unsigned)blocks, (unsigned)n_tiles);
+#ifdef STM_DCN_EXPERIMENTS
+  if (const char* e = getenv("STM_DCN_DBG")) {          // bring-up experiments only (wrong results by design)
+    const int v = atoi(e);
+    if (m_tiles == 2 && v == 1) return launch_t<2, 1>(args, tmap, grid, smem_bytes, stream);
+    if (m_tiles == 2 && v == 2) return launch_t<2, 2>(args, tmap, grid, smem_bytes, stream);
+    if (m_tiles == 2 && v == 3) return launch_t<2, 3>(args, tmap, grid, smem_bytes, stream);
+  }
+#endif
   if (m_tiles == 2) return launch_t<2>(args, tmap, grid, smem_bytes, stream);
   return launch_t<1>(args, tmap, grid, smem_bytes, stream);
 }

@@ -166,6 +166,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return r;
 }
 
+// d = bf16(a) * bf16(b) + c in fp32 (SASS FHFMA.BF16 with .H0/.H1 operand selectors: the bf16 halves of a
+// packed word feed the FMA directly, no unpack instruction)
+__device__ __forceinline__ float fma_bf16(uint16_t a, uint16_t b, float c) {
+  float r;
+  asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(r) : "h"(a), "h"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ void split16(uint32_t x, uint16_t& lo, uint16_t& hi) {
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(lo), "=h"(hi) : "r"(x));
+}
+
 }  // namespace tc
 
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
