@@ -72,7 +72,7 @@ struct SmemLayout {
     int off = stages * stage_bytes;
     meta_w = off; off += 2 * ROWS * 16;
     meta_o = off; off += 2 * ROWS * 16;
-    row_x = off;  off += ROWS * 8;
+    row_x = off;  off += ROWS * 8;   // (kept 8 B/row: uint32 batch offset in elements + pad)
     row_y = off;  off += ROWS * 8;
     row_pos = off; off += ROWS * 16;
     bars = off;   off += (2 * MAX_STAGES + 2) * 8;
@@ -91,7 +91,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   const SmemLayout<M_TILES> L(a.block_n, a.stages);
   uint4* meta_w = reinterpret_cast<uint4*>(smem + L.meta_w);    // {w0|w1, w2|w3 as bf16 pairs, nonzero-corner bits, -}
   int4* meta_o = reinterpret_cast<int4*>(smem + L.meta_o);
-  const __nv_bfloat16** row_x = reinterpret_cast<const __nv_bfloat16**>(smem + L.row_x);
+  uint32_t* row_x = reinterpret_cast<uint32_t*>(smem + L.row_x);     // element offset of x[b, 0, 0, 0] from the problem base
   int64_t* row_y = reinterpret_cast<int64_t*>(smem + L.row_y);
   int4* row_pos = reinterpret_cast<int4*>(smem + L.row_pos);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -127,7 +127,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       yb = b * pr.y_sn + ho * pr.y_sh + wo * pr.y_sw;
       valid = 1;
     }
-    row_x[tid] = reinterpret_cast<const __nv_bfloat16*>(pr.x) + b * pr.x_sn;
+    row_x[tid] = (uint32_t)(b * pr.x_sn);
     row_y[tid] = yb;
     row_pos[tid] = make_int4(b, ho, wo, valid);
   }
@@ -163,6 +163,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     const bool has_off = pr.offset != nullptr, has_mask = pr.mask != nullptr;
     const bool off_bf16 = (p.flags & 0x100) != 0;      // internal flag: offsets/masks stored as bf16
     const int4 pos = (tid < ROWS) ? row_pos[tid] : make_int4(0, 0, 0, 0);
+    const __nv_bfloat16* __restrict__ xbase = reinterpret_cast<const __nv_bfloat16*>(pr.x);
     const int n_iter = K * p.dg;
 
     // raw (dy, dx, mask) of this thread's row for iteration `it`; issued one iteration ahead so the
@@ -198,13 +199,13 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     auto issue = [&](GTask& t, int buf, int row, int chan, uint32_t a_stage) {
       const uint4 mw = meta_w[buf * ROWS + row];
       const int4 o4 = meta_o[buf * ROWS + row];
-      const __nv_bfloat16* xb = row_x[row] + chan;
+      const uint32_t eb = row_x[row] + (uint32_t)chan;     // 32-bit element offsets from the problem base (host checks < 2^31)
       t.w01 = mw.x; t.w23 = mw.y;
       t.dst = a_stage + row * 128 + swz;                 // row r of the (stacked) A tiles lives at r * 128
-      const uint4* s0 = reinterpret_cast<const uint4*>(xb + o4.x);
-      const uint4* s1 = reinterpret_cast<const uint4*>(xb + o4.y);
-      const uint4* s2 = reinterpret_cast<const uint4*>(xb + o4.z);
-      const uint4* s3 = reinterpret_cast<const uint4*>(xb + o4.w);
+      const uint4* s0 = reinterpret_cast<const uint4*>(xbase + (eb + (uint32_t)o4.x));
+      const uint4* s1 = reinterpret_cast<const uint4*>(xbase + (eb + (uint32_t)o4.y));
+      const uint4* s2 = reinterpret_cast<const uint4*>(xbase + (eb + (uint32_t)o4.z));
+      const uint4* s3 = reinterpret_cast<const uint4*>(xbase + (eb + (uint32_t)o4.w));
       // every lane's four corners carry weight (the common, interior case): plain loads.  Otherwise
       // zero-weight corners are NOT read, so data outside the sample can never leak in (0 * Inf).
       if (DBG == 1) {
@@ -449,6 +450,7 @@ bool dcn_tc_supported(const StmDcnConv* c, const StmDcnProblem* pr, int n, const
     const StmDcnProblem& q = pr[i];
     if (q.batch == 0) continue;
     if (((uintptr_t)q.x & 15) || ((uintptr_t)q.y & 15)) { *why = "x / y not 16-byte aligned"; return false; }
+    if ((int64_t)q.batch * q.x_stride_n >= (1ll << 31)) { *why = "x spans more than 2^31 elements"; return false; }
     if ((q.x_stride_n | q.x_stride_h | q.x_stride_w | q.y_stride_n | q.y_stride_h | q.y_stride_w) & 7) {
       *why = "x / y strides not multiples of 8 elements";
       return false;
