@@ -4,17 +4,18 @@
 //   A[m, (tap, c)] = mask[m, tap] * bilinear(x[b, :, :, c], p(m) + tap + offset[m, tap])
 //
 // A is never written to global memory.  Per CTA (256 or 128 output pixels x one N tile of <= 256):
-//   * warps 0-15 PRODUCERS: once per (tap, deformable group) compute the four bilinear corner
-//                weights/offsets of every row (DCN border rule, mask folded in) into shared memory;
-//                then per 64-channel K block gather 4 x 16-byte corner vectors per (row, 8 channels)
-//                (NHWC => contiguous), blend with fp32 accumulation (FHFMA.BF16: bf16 corner weights, no
-//                unpack instructions), round once to bf16 and store into the
-//                128B-swizzled K-major A tile; fence.proxy.async + mbarrier arrive.
-//                After the main loop the same warps run the EPILOGUE: tcgen05.ld the fp32
-//                accumulators, + bias, ReLU, bf16, 16-byte stores to NHWC y.
-//   * warp 16    TMA: the matching [N x 64] slice of the packed OHWI weight -> swizzled B tile.
-//   * warp 17    MMA: one thread issues tcgen05.mma (M=128, N<=256, K=16, bf16 -> fp32 in TMEM),
-//                tcgen05.commit frees the stage; owns the TMEM allocation.
+//   * producer warps (16, or 8 with a deeper look-ahead): one tap ahead of the gather, all threads compute
+//                the four corner POINTERS (64-bit; corners without weight point at a zero page, so the
+//                gather needs no predicates) and bf16 corner weights (DCN border rule, mask folded in) of
+//                every row into triple-buffered shared memory.  Per 64-channel K block every thread runs a
+//                register-pipelined stream of gather tasks: 4 x 16-byte corner loads (NHWC => contiguous),
+//                fp32 blend (FHFMA.BF16: bf16 data and weights feed the FMA directly), one rounding to
+//                bf16, 16-byte store into the 128B-swizzled K-major A tile; one mbarrier arrive per warp.
+//                Afterwards the same warps are the EPILOGUE: tcgen05.ld the fp32 accumulators, + bias,
+//                ReLU, bf16, 16-byte stores to NHWC y.
+//   * TMA warp:  the matching [N x 64] slice of the packed OHWI weight -> swizzled B tile.
+//   * MMA warp:  one thread issues fence.proxy.async + tcgen05.mma (M=128, N<=256, K=16, bf16 -> fp32 in
+//                TMEM), tcgen05.commit frees the stage; owns the TMEM allocation.
 // Several feature maps that share a weight (FPN levels) are tiles of ONE launch.
 //
 // Replaces modulated_deformable_im2col + per-sample SGEMM of dcn_v2 / mmcv (reference
@@ -49,11 +50,15 @@ using namespace tc;
 constexpr int BLOCK_K = 64;             // bf16 elements = one 128-byte swizzle row
 constexpr int TILE_M = 128;             // rows per accumulator (UMMA M)
 constexpr int A_TILE_BYTES = TILE_M * 128;
-constexpr int PRODUCER_WARPS = 16;
-constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;
-constexpr int NUM_THREADS = PRODUCER_THREADS + 64;
 constexpr int MAX_STAGES = 6;
+constexpr int META_BUFS = 3;            // sample metadata is computed one tap ahead of the gather that reads it
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int ZERO_PAGE_BYTES = 4096;   // >= 2 * in_c (dcn_tc_supported caps in_c at 2048)
+
+// Corners that carry no weight (outside the map, outside the sample's support, rows past the end of the
+// problem) are pointed here instead of being predicated off: the gather stays branch-free and 0 * 0 = 0,
+// so nothing outside a sample's support can leak into it.
+__device__ __align__(128) unsigned char g_zero_page[ZERO_PAGE_BYTES + 128];
 
 struct TcArgs {
   DcnParams p;
@@ -66,34 +71,46 @@ struct TcArgs {
 template <int M_TILES>
 struct SmemLayout {
   static constexpr int ROWS = TILE_M * M_TILES;
-  int stage_bytes, meta_w, meta_o, row_x, row_y, row_pos, bars, total;
+  int stage_bytes, meta_p, meta_w, bars, total;
   __host__ __device__ SmemLayout(int block_n, int stages) {
     stage_bytes = M_TILES * A_TILE_BYTES + block_n * 128;
     int off = stages * stage_bytes;
-    meta_w = off; off += 2 * ROWS * 16;
-    meta_o = off; off += 2 * ROWS * 16;
-    row_x = off;  off += ROWS * 8;   // (kept 8 B/row: uint32 batch offset in elements + pad)
-    row_y = off;  off += ROWS * 8;
-    row_pos = off; off += ROWS * 16;
+    meta_p = off; off += META_BUFS * ROWS * 32;    // four 64-bit corner pointers per row
+    meta_w = off; off += META_BUFS * ROWS * 8;     // four bf16 corner weights per row
     bars = off;   off += (2 * MAX_STAGES + 2) * 8;
     total = off + 1024;   // slack for manual 1024-byte alignment of the base
   }
 };
 
-template <int M_TILES, int DBG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__device__ __forceinline__ uint4 ldg_nc_v4(uint64_t addr) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(addr));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_wide(uint32_t lo, uint32_t hi, uint32_t off) {
+  uint64_t r;
+  const uint64_t base = ((uint64_t)hi << 32) | lo;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off), "l"(base));
+  return r;
+}
+
+// PW producer warps (8 or 16) + 1 TMA warp + 1 MMA warp.  CFENCE: the generic->async proxy fence for the
+// A tile is executed by the MMA thread after it has acquired the stage (instead of by every producer
+// thread before its release): a producer-side fence.proxy.async compiles to MEMBAR.ALL.CTA, which also
+// waits for the gather loads that are already in flight for the NEXT K block and drains the pipeline.
+template <int M_TILES, int PW, int D, bool CFENCE>
+__global__ void __launch_bounds__(PW * 32 + 64, 1)
 dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap tmap_w) {
   constexpr int ROWS = TILE_M * M_TILES;
-  constexpr int ROWS_PER_PASS = PRODUCER_WARPS * 4;     // 64 rows per sweep of the producer warps
-  constexpr int PASSES = ROWS / ROWS_PER_PASS;
+  constexpr int PT = PW * 32;                           // producer threads
+  constexpr int ROWS_PER_PASS = PW * 4;                 // rows covered by one sweep of the producer warps
+  constexpr int TPK = ROWS / ROWS_PER_PASS;             // gather tasks per thread per K block
+  constexpr int CPT = 4 * ROWS / PT;                    // corners per thread when computing sample metadata
+  static_assert(CPT == 1 || CPT == 2 || CPT == 4, "metadata split");
+  static_assert(D >= 1 && D <= TPK && TPK % D == 0, "gather look-ahead must divide the tasks per K block");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const SmemLayout<M_TILES> L(a.block_n, a.stages);
-  uint4* meta_w = reinterpret_cast<uint4*>(smem + L.meta_w);    // {w0|w1, w2|w3 as bf16 pairs, nonzero-corner bits, -}
-  int4* meta_o = reinterpret_cast<int4*>(smem + L.meta_o);
-  uint32_t* row_x = reinterpret_cast<uint32_t*>(smem + L.row_x);     // element offset of x[b, 0, 0, 0] from the problem base
-  int64_t* row_y = reinterpret_cast<int64_t*>(smem + L.row_y);
-  int4* row_pos = reinterpret_cast<int4*>(smem + L.row_pos);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* accum_bar = empty_bar + MAX_STAGES;
@@ -114,33 +131,16 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   const int m0 = ((int)blockIdx.x - pr.tile_begin) * ROWS;
 
   // ---- one-time setup ----
-  if (tid < ROWS) {
-    const int m = m0 + tid;
-    int b = 0, ho = 0, wo = 0, valid = 0;
-    int64_t yb = -1;
-    if (m < pr.m_total) {
-      const int hw = pr.out_h * pr.out_w;
-      b = m / hw;
-      const int r = m - b * hw;
-      ho = r / pr.out_w;
-      wo = r - ho * pr.out_w;
-      yb = b * pr.y_sn + ho * pr.y_sh + wo * pr.y_sw;
-      valid = 1;
-    }
-    row_x[tid] = (uint32_t)(b * pr.x_sn);
-    row_y[tid] = yb;
-    row_pos[tid] = make_int4(b, ho, wo, valid);
-  }
-  if (warp == PRODUCER_WARPS && lane == 0) {
+  if (warp == PW && lane == 0) {
     prefetch_tensormap(&tmap_w);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], PRODUCER_WARPS + 1);   // producer warps + the TMA thread's expect_tx arrive
+      mbar_init(&full_bar[s], PW + 1);               // producer warps + the TMA thread's expect_tx arrive
       mbar_init(&empty_bar[s], 1);                   // tcgen05.commit
     }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == PRODUCER_WARPS + 1) {
+  if (warp == PW + 1) {
     tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
     tmem_relinquish();
   }
@@ -152,75 +152,132 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   const int K = p.kh * p.kw;
   const int cpd = p.in_c / p.dg;            // channels per deformable group (multiple of 64)
   const int chunks = cpd / BLOCK_K;
+  const int n_iter = K * p.dg;              // (tap, deformable group) pairs, tap-major
+  const int num_kb = n_iter * chunks;
 
-  if (warp < PRODUCER_WARPS) {
+  if (warp < PW) {
     // =============================== PRODUCERS ===============================
     const int v = lane & 7;                 // 16-byte (8-channel) slot inside the 64-channel K block
-    const int rsub = lane >> 3;             // 4 rows per warp instruction
-    const int row0 = warp * 4 + rsub;       // this thread's row in pass 0; pass j adds j * ROWS_PER_PASS
+    const int row0 = warp * 4 + (lane >> 3);       // this thread's row in pass 0; pass j adds j * ROWS_PER_PASS
     // 128B swizzle: chunk v of row r goes to chunk v ^ (r & 7); r & 7 is the same in every pass
-    const int swz = (v ^ (row0 & 7)) << 4;
+    const uint32_t dst_off = (uint32_t)(row0 * 128 + ((v ^ (row0 & 7)) << 4));
+    const uint32_t mp_addr = smem_u32(smem + L.meta_p) + (uint32_t)row0 * 32u;
+    const uint32_t mw_addr = smem_u32(smem + L.meta_w) + (uint32_t)row0 * 8u;
+
+    // ---- sample metadata: thread -> (row, CPT of its 4 corners) ----
+    const int mrow = tid % ROWS, cg = tid / ROWS;
     const bool has_off = pr.offset != nullptr, has_mask = pr.mask != nullptr;
     const bool off_bf16 = (p.flags & 0x100) != 0;      // internal flag: offsets/masks stored as bf16
-    const int4 pos = (tid < ROWS) ? row_pos[tid] : make_int4(0, 0, 0, 0);
-    const __nv_bfloat16* __restrict__ xbase = reinterpret_cast<const __nv_bfloat16*>(pr.x);
-    const int n_iter = K * p.dg;
+    const bool mask_sig = has_mask && (p.flags & STM_DCN_MASK_SIGMOID);
+    int hb = 0, wb = 0;                     // top-left of the un-deformed receptive field
+    bool rvalid = false;
+    int64_t off_base = 0, mask_base = 0;
+    const __nv_bfloat16* ximg = reinterpret_cast<const __nv_bfloat16*>(pr.x);
+    {
+      const int m = m0 + mrow;
+      if (m < pr.m_total) {
+        const int hw = pr.out_h * pr.out_w;
+        const int b = m / hw;
+        const int r = m - b * hw;
+        const int ho = r / pr.out_w, wo = r - ho * pr.out_w;
+        rvalid = true;
+        hb = ho * p.sh - p.ph;
+        wb = wo * p.sw - p.pw;
+        ximg += (int64_t)b * pr.x_sn;
+        off_base = b * pr.off_sn + ho * pr.off_sh + wo * pr.off_sw;
+        mask_base = b * pr.mask_sn + ho * pr.mask_sh + wo * pr.mask_sw;
+      }
+    }
+    const uint64_t zero_page = reinterpret_cast<uint64_t>(g_zero_page);
 
-    // raw (dy, dx, mask) of this thread's row for iteration `it`; issued one iteration ahead so the
-    // global-load latency hides behind the gather instead of stalling everybody at the named barrier
+    // raw (dy, dx, mask) of this thread's row for iteration `it`; issued one iteration ahead of its use
     auto load_raw = [&](int it_, float& oy, float& ox, float& mk) {
       oy = 0.f; ox = 0.f; mk = 1.f;
-      if (tid >= ROWS || !pos.w || it_ >= n_iter) return;
+      if (!rvalid || it_ >= n_iter) return;
       const int tap_ = it_ / p.dg, g_ = it_ - tap_ * p.dg;
       if (has_off) {
-        const int64_t o = pos.x * pr.off_sn + (int64_t)(g_ * 2 * K + 2 * tap_) * pr.off_sc + pos.y * pr.off_sh + pos.z * pr.off_sw;
+        const int64_t o = off_base + (int64_t)(g_ * 2 * K + 2 * tap_) * pr.off_sc;
         if (off_bf16) {
-          oy = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.offset)[o]);
-          ox = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.offset)[o + pr.off_sc]);
+          oy = __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(pr.offset) + o));
+          ox = __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(pr.offset) + o + pr.off_sc));
         } else {
-          oy = reinterpret_cast<const float*>(pr.offset)[o];
-          ox = reinterpret_cast<const float*>(pr.offset)[o + pr.off_sc];
+          oy = __ldg(reinterpret_cast<const float*>(pr.offset) + o);
+          ox = __ldg(reinterpret_cast<const float*>(pr.offset) + o + pr.off_sc);
         }
       }
       if (has_mask) {
-        const int64_t o = pos.x * pr.mask_sn + (int64_t)(g_ * K + tap_) * pr.mask_sc + pos.y * pr.mask_sh + pos.z * pr.mask_sw;
-        mk = off_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(pr.mask)[o])
-                      : reinterpret_cast<const float*>(pr.mask)[o];
+        const int64_t o = mask_base + (int64_t)(g_ * K + tap_) * pr.mask_sc;
+        mk = off_bf16 ? __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(pr.mask) + o))
+                      : __ldg(reinterpret_cast<const float*>(pr.mask) + o);
+      }
+    };
+    // DCN border rule: the sample is 0 outside (-1, H) x (-1, W); corners outside the map add 0.
+    auto compute_meta = [&](int it_, float oy, float ox, float mk) {
+      const int buf = it_ % META_BUFS;
+      const int tap_ = it_ / p.dg, g_ = it_ - tap_ * p.dg;
+      const int ti = tap_ / p.kw, tj = tap_ - ti * p.kw;
+      const float h = (float)(hb + ti * p.dh) + oy;
+      const float w = (float)(wb + tj * p.dw) + ox;
+      const bool inside = rvalid && h > -1.f && w > -1.f && h < (float)pr.in_h && w < (float)pr.in_w;
+      const float hf = floorf(h), wf = floorf(w);
+      const int h0 = (int)hf, w0 = (int)wf;
+      const float lh = h - hf, lw = w - wf;
+      const float scale = mask_sig ? sigmoidf_(mk) : mk;
+      uint64_t ptr[CPT];
+      uint32_t wt[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        const int c = cg * CPT + i;                       // corner: bit 1 = lower row, bit 0 = right column
+        const int yy = h0 + (c >> 1), xx = w0 + (c & 1);
+        const float wy = (c >> 1) ? lh : 1.f - lh, wx = (c & 1) ? lw : 1.f - lw;
+        const bool ok = inside && yy >= 0 && yy < pr.in_h && xx >= 0 && xx < pr.in_w;
+        uint32_t wb16 = ok ? (pack_bf16(wy * wx * scale, 0.f) & 0xffffu) : 0u;
+        const bool live = (wb16 & 0x7fffu) != 0u;
+        if (!live) wb16 = 0u;
+        ptr[i] = live ? reinterpret_cast<uint64_t>(ximg + ((int64_t)yy * pr.x_sh + (int64_t)xx * pr.x_sw + g_ * cpd)) : zero_page;
+        wt[i] = wb16;
+      }
+      uint8_t* mpd = smem + L.meta_p + ((buf * ROWS + mrow) * 32 + cg * CPT * 8);
+      uint8_t* mwd = smem + L.meta_w + ((buf * ROWS + mrow) * 8 + cg * CPT * 2);
+      if (CPT == 4) {
+        reinterpret_cast<uint4*>(mpd)[0] = make_uint4((uint32_t)ptr[0], (uint32_t)(ptr[0] >> 32), (uint32_t)ptr[1], (uint32_t)(ptr[1] >> 32));
+        reinterpret_cast<uint4*>(mpd)[1] = make_uint4((uint32_t)ptr[2 % CPT], (uint32_t)(ptr[2 % CPT] >> 32), (uint32_t)ptr[3 % CPT], (uint32_t)(ptr[3 % CPT] >> 32));
+        *reinterpret_cast<uint2*>(mwd) = make_uint2(wt[0] | (wt[1 % CPT] << 16), wt[2 % CPT] | (wt[3 % CPT] << 16));
+      } else if (CPT == 2) {
+        *reinterpret_cast<uint4*>(mpd) = make_uint4((uint32_t)ptr[0], (uint32_t)(ptr[0] >> 32), (uint32_t)ptr[1 % CPT], (uint32_t)(ptr[1 % CPT] >> 32));
+        *reinterpret_cast<uint32_t*>(mwd) = wt[0] | (wt[1 % CPT] << 16);
+      } else {
+        *reinterpret_cast<uint2*>(mpd) = make_uint2((uint32_t)ptr[0], (uint32_t)(ptr[0] >> 32));
+        *reinterpret_cast<uint16_t*>(mwd) = (uint16_t)wt[0];
       }
     };
 
-    // One gather task = (row, 8 channels) of one K block: 4 corner loads, fp32 blend, one 16-byte store.
-    // Two register sets (A, B) rotate so the loads of task t+1 are in flight while task t is blended.
+    // One gather task = (row, 8 channels) of one K block: 4 corner loads, fp32 blend (FHFMA.BF16: bf16 data and
+    // weights feed the FMA directly), one rounding to bf16, one 16-byte store.  Every thread keeps the TPK
+    // tasks of the NEXT K block in flight while it blends and stores the current one.
     struct GTask {
       uint32_t w01, w23;   // bf16 corner weights (w0 | w1 << 16, w2 | w3 << 16)
-      uint32_t dst;        // shared-memory address of this task's 16-byte slot in the A tile
       uint4 c[4];
     };
-    auto issue = [&](GTask& t, int buf, int row, int chan, uint32_t a_stage) {
-      const uint4 mw = meta_w[buf * ROWS + row];
-      const int4 o4 = meta_o[buf * ROWS + row];
-      const uint32_t eb = row_x[row] + (uint32_t)chan;     // 32-bit element offsets from the problem base (host checks < 2^31)
-      t.w01 = mw.x; t.w23 = mw.y;
-      t.dst = a_stage + row * 128 + swz;                 // row r of the (stacked) A tiles lives at r * 128
-      const uint4* s0 = reinterpret_cast<const uint4*>(xbase + (eb + (uint32_t)o4.x));
-      const uint4* s1 = reinterpret_cast<const uint4*>(xbase + (eb + (uint32_t)o4.y));
-      const uint4* s2 = reinterpret_cast<const uint4*>(xbase + (eb + (uint32_t)o4.z));
-      const uint4* s3 = reinterpret_cast<const uint4*>(xbase + (eb + (uint32_t)o4.w));
-      // every lane's four corners carry weight (the common, interior case): plain loads.  Otherwise
-      // zero-weight corners are NOT read, so data outside the sample can never leak in (0 * Inf).
-      if (DBG == 1) {
-        t.c[0] = t.c[1] = t.c[2] = t.c[3] = make_uint4((uint32_t)(uintptr_t)s0, (uint32_t)(uintptr_t)s1, (uint32_t)(uintptr_t)s2, (uint32_t)(uintptr_t)s3);
-      } else if (__all_sync(0xffffffffu, mw.z == 15u)) {
-        t.c[0] = __ldg(s0); t.c[1] = __ldg(s1); t.c[2] = __ldg(s2); t.c[3] = __ldg(s3);
-      } else {
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        t.c[0] = (mw.z & 1u) ? __ldg(s0) : z;
-        t.c[1] = (mw.z & 2u) ? __ldg(s1) : z;
-        t.c[2] = (mw.z & 4u) ? __ldg(s2) : z;
-        t.c[3] = (mw.z & 8u) ? __ldg(s3) : z;
-      }
+    struct GMeta {
+      uint4 p01, p23;
+      uint2 w;
     };
-    auto finish = [&](const GTask& t) {
+    auto read_meta = [&](GMeta& m, int buf, int j) {
+      const uint32_t pa = mp_addr + (uint32_t)((buf * ROWS + j * ROWS_PER_PASS) * 32);
+      const uint32_t wa = mw_addr + (uint32_t)((buf * ROWS + j * ROWS_PER_PASS) * 8);
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m.p01.x), "=r"(m.p01.y), "=r"(m.p01.z), "=r"(m.p01.w) : "r"(pa));
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m.p23.x), "=r"(m.p23.y), "=r"(m.p23.z), "=r"(m.p23.w) : "r"(pa + 16u));
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(m.w.x), "=r"(m.w.y) : "r"(wa));
+    };
+    auto issue = [&](GTask& t, const GMeta& m, uint32_t coff) {
+      t.w01 = m.w.x; t.w23 = m.w.y;
+      t.c[0] = ldg_nc_v4(add_wide(m.p01.x, m.p01.y, coff));
+      t.c[1] = ldg_nc_v4(add_wide(m.p01.z, m.p01.w, coff));
+      t.c[2] = ldg_nc_v4(add_wide(m.p23.x, m.p23.y, coff));
+      t.c[3] = ldg_nc_v4(add_wide(m.p23.z, m.p23.w, coff));
+    };
+    auto finish = [&](const GTask& t, uint32_t dst) {
       const uint32_t* q0 = reinterpret_cast<const uint32_t*>(&t.c[0]);
       const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&t.c[1]);
       const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&t.c[2]);
@@ -246,92 +303,100 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
         hi = fma_bf16(d1, w3, hi);
         o[i] = pack_bf16(lo, hi);
       }
-      if (DBG == 3) { o[0] = q0[0]; o[1] = q0[1]; o[2] = q0[2]; o[3] = q0[3]; }
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t.dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-    };
-    auto publish = [&](int stage) {        // this warp's part of the A tile of `stage` is complete
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]));
     };
 
-    GTask A, B;
-    int stage = 0, prev_stage = 0;
-    uint32_t phase = 0;
-    bool pending = false;                   // B holds the last task of the previous K block
+    GTask S[D];                             // task (kb, j) lives in S[j % D]; D tasks are in flight per thread
     float r_oy, r_ox, r_mk;
+    // prologue: metadata of iteration 0, then the first D gather tasks of K block 0
     load_raw(0, r_oy, r_ox, r_mk);
-#pragma unroll 1
-    for (int it = 0; it < n_iter; ++it) {
-      const int tap = it / p.dg, g = it - tap * p.dg;
-      const int ti = tap / p.kw, tj = tap - ti * p.kw;
-      const int buf = it & 1;
-      if (tid < ROWS) {
-        Sample4 sm;
+    compute_meta(0, r_oy, r_ox, r_mk);
+    load_raw(1, r_oy, r_ox, r_mk);
+    named_barrier_sync(1, PT);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { sm.w[i] = 0.f; sm.o[i] = 0; }
-        if (pos.w) {
-          const float mk = (has_mask && (p.flags & STM_DCN_MASK_SIGMOID)) ? sigmoidf_(r_mk) : r_mk;
-          const float h = (float)(pos.y * p.sh - p.ph + ti * p.dh) + r_oy;
-          const float w = (float)(pos.z * p.sw - p.pw + tj * p.dw) + r_ox;
-          sm = make_sample(h, w, pr.in_h, pr.in_w, pr.x_sh, pr.x_sw, mk);
-        }
-        {
-          const uint32_t w01 = pack_bf16(sm.w[0], sm.w[1]), w23 = pack_bf16(sm.w[2], sm.w[3]);
-          const uint32_t nz = ((w01 & 0x7fffu) ? 1u : 0u) | ((w01 & 0x7fff0000u) ? 2u : 0u) | ((w23 & 0x7fffu) ? 4u : 0u) |
-                              ((w23 & 0x7fff0000u) ? 8u : 0u);
-          meta_w[buf * ROWS + tid] = make_uint4(w01, w23, nz, 0u);
-        }
-        meta_o[buf * ROWS + tid] = make_int4(sm.o[0], sm.o[1], sm.o[2], sm.o[3]);
-      }
-      load_raw(it + 1, r_oy, r_ox, r_mk);
-      // meta[buf] was last read two iterations ago; every thread has passed the previous barrier since
-      named_barrier_sync(1, PRODUCER_THREADS);
-#pragma unroll 1
-      for (int cc = 0; cc < chunks; ++cc) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        const uint32_t a_stage = smem_u32(smem + stage * L.stage_bytes);
-        const int chan = g * cpd + cc * BLOCK_K + v * 8;
-#pragma unroll
-        for (int j = 0; j < PASSES; j += 2) {
-          issue(A, buf, row0 + j * ROWS_PER_PASS, chan, a_stage);
-          if (j == 0) {
-            if (pending) { finish(B); publish(prev_stage); }
-          } else {
-            finish(B);
-          }
-          issue(B, buf, row0 + (j + 1) * ROWS_PER_PASS, chan, a_stage);
-          finish(A);
-        }
-        pending = true;
-        prev_stage = stage;
-        if (++stage == stages) { stage = 0; phase ^= 1u; }
-      }
+    for (int j = 0; j < D; ++j) {
+      GMeta m;
+      read_meta(m, 0, j);
+      issue(S[j], m, (uint32_t)(v * 16));
     }
-    if (pending) { finish(B); publish(prev_stage); }
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0, cc = 0;                     // (tap, group) iteration and channel chunk of the CURRENT K block
+#pragma unroll 1
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (cc == 0 && it + 1 < n_iter) {
+        // metadata one iteration ahead: buffer (it+1) % 3 was last read by the gather of iteration it-2, which
+        // every thread finished before it arrived at the previous barrier
+        compute_meta(it + 1, r_oy, r_ox, r_mk);
+        load_raw(it + 2, r_oy, r_ox, r_mk);
+        named_barrier_sync(1, PT);
+      }
+      int nit = it, ncc = cc + 1;
+      if (ncc == chunks) { ncc = 0; nit = it + 1; }
+      const bool has_next = kb + 1 < num_kb;
+      const int cbuf = it % META_BUFS, nbuf = nit % META_BUFS;
+      const uint32_t ccoff = (uint32_t)((cc * BLOCK_K + v * 8) * 2), ncoff = (uint32_t)((ncc * BLOCK_K + v * 8) * 2);
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      const uint32_t a_dst = smem_u32(smem + stage * L.stage_bytes) + dst_off;
+      // step j: blend + store task (kb, j), then refill its register set with task j + D of this K block or,
+      // past the end, task j + D - TPK of the next one
+      GMeta m;
+      if (D < TPK) read_meta(m, cbuf, D);
+      else if (has_next) read_meta(m, nbuf, 0);
+#pragma unroll
+      for (int j = 0; j < TPK; ++j) {
+        const bool cur = j + D < TPK;                                   // compile-time after unrolling
+        const bool ncur = j + 1 + D < TPK;
+        GMeta mn;
+        if (j + 1 < TPK) {
+          if (ncur) read_meta(mn, cbuf, j + 1 + D);
+          else if (has_next) read_meta(mn, nbuf, j + 1 + D - TPK);
+        }
+        finish(S[j % D], a_dst + (uint32_t)(j * ROWS_PER_PASS * 128));
+        if (cur) issue(S[j % D], m, ccoff);
+        else if (has_next) issue(S[j % D], m, ncoff);
+        if (j + 1 < TPK) m = mn;
+      }
+      // this warp's part of the A tile of `stage` is complete
+      if (!CFENCE) fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      if (++stage == stages) { stage = 0; phase ^= 1u; }
+      it = nit; cc = ncc;
+    }
     // =============================== EPILOGUE ===============================
     mbar_wait(accum_bar, 0);
     tcgen05_fence_after();
-    // warp w may only touch TMEM lanes [32 (w % 4), +32).  The four warp groups (w / 4) split the
-    // accumulators: M_TILES == 2 -> (tile, column half); M_TILES == 1 -> column quarter.
+    // warp w may only touch TMEM lanes [32 (w % 4), +32).  The PW / 4 warp groups split the accumulators:
+    // M_TILES == 2 -> (tile, column part); M_TILES == 1 -> column part.
+    constexpr int NG = PW / 4;
     const int q = warp & 3;
     const int grp = warp >> 2;
     const int mt = (M_TILES == 2) ? (grp & 1) : 0;
     const int part = (M_TILES == 2) ? (grp >> 1) : grp;
-    constexpr int PARTS = (M_TILES == 2) ? 2 : 4;
+    constexpr int PARTS = (M_TILES == 2) ? NG / 2 : NG;
     const int nchunk = block_n / 16;
     const int c_begin = (part * nchunk / PARTS) * 16;
     const int c_end = ((part + 1) * nchunk / PARTS) * 16;
     const int row = mt * TILE_M + q * 32 + lane;
-    const int64_t yoff = row_y[row];
-    __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(pr.y) + (yoff >= 0 ? yoff : 0) + n0;
+    const int m = m0 + row;
+    const bool row_ok = m < pr.m_total;
+    int64_t yoff = 0;
+    if (row_ok) {
+      const int hw = pr.out_h * pr.out_w;
+      const int b = m / hw;
+      const int r = m - b * hw;
+      const int ho = r / pr.out_w, wo = r - ho * pr.out_w;
+      yoff = b * pr.y_sn + ho * pr.y_sh + wo * pr.y_sw;
+    }
+    __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(pr.y) + yoff + n0;
     const bool relu = (p.flags & STM_DCN_RELU) != 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * block_n);
     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
       uint32_t acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
       tmem_ld_wait();
-      if (yoff >= 0) {
+      if (row_ok) {
         uint32_t o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -348,7 +413,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
       }
     }
-  } else if (warp == PRODUCER_WARPS) {
+  } else if (warp == PW) {
     // =============================== TMA (weights) ===============================
     if (lane == 0) {
       int s = 0;
@@ -370,12 +435,12 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(TILE_M, (uint32_t)block_n);
-      const int num_kb = K * p.dg * chunks;
       int s = 0;
       uint32_t phase = 0;
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait_relaxed(&full_bar[s], phase);
+        if (CFENCE) fence_proxy_async_smem();   // producers' st.shared (acquired above) -> visible to the UMMA reads
         tcgen05_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * L.stage_bytes);
         const uint64_t bdesc = umma_desc_sw128(a_addr + M_TILES * A_TILE_BYTES);
@@ -384,7 +449,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
           const uint64_t adesc = umma_desc_sw128(a_addr + mt * A_TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
-            if (DBG != 2) umma_bf16(tmem_base + (uint32_t)(mt * block_n), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+            umma_bf16(tmem_base + (uint32_t)(mt * block_n), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                       (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);          // stage reusable once these MMAs have read it
@@ -398,10 +463,15 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   // ---- teardown ----
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == PRODUCER_WARPS + 1) {
+  if (warp == PW + 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 int pick_block_n(int out_c) {
@@ -424,14 +494,14 @@ int sm_count() {
   return n;
 }
 
-template <int M_TILES, int DBG = 0>
+template <int M_TILES, int PW, int D, bool CFENCE>
 int launch_t(const TcArgs& args, const CUtensorMap& tmap, dim3 grid, int smem_bytes, cudaStream_t stream) {
   static int configured = 0;
   if (configured < smem_bytes) {
-    STM_CUDA_OK(cudaFuncSetAttribute(dcn_tc_kernel<M_TILES, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    STM_CUDA_OK(cudaFuncSetAttribute(dcn_tc_kernel<M_TILES, PW, D, CFENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = smem_bytes;
   }
-  dcn_tc_kernel<M_TILES, DBG><<<grid, NUM_THREADS, smem_bytes, stream>>>(args, tmap);
+  dcn_tc_kernel<M_TILES, PW, D, CFENCE><<<grid, PW * 32 + 64, smem_bytes, stream>>>(args, tmap);
   count_launch();
   STM_CUDA_OK(cudaGetLastError());
   return STM_OK;
@@ -443,6 +513,7 @@ bool dcn_tc_supported(const StmDcnConv* c, const StmDcnProblem* pr, int n, const
   *why = "";
   if (c->dtype != STM_BF16) { *why = "dtype is not bf16"; return false; }
   if (c->groups != 1) { *why = "groups != 1"; return false; }
+  if (2 * c->in_c > ZERO_PAGE_BYTES) { *why = "in_c > 2048"; return false; }
   if (c->in_c % 64 != 0 || (c->in_c / c->deform_groups) % 64 != 0) { *why = "channels per deformable group not a multiple of 64"; return false; }
   if (c->out_c % 16 != 0 || pick_block_n(c->out_c) == 0) { *why = "out_c not tileable (multiple of 16, <= 256 or a multiple of 128)"; return false; }
   if (c->kernel_h * c->kernel_w > 64) { *why = "kernel too large"; return false; }
@@ -450,7 +521,6 @@ bool dcn_tc_supported(const StmDcnConv* c, const StmDcnProblem* pr, int n, const
     const StmDcnProblem& q = pr[i];
     if (q.batch == 0) continue;
     if (((uintptr_t)q.x & 15) || ((uintptr_t)q.y & 15)) { *why = "x / y not 16-byte aligned"; return false; }
-    if ((int64_t)q.batch * q.x_stride_n >= (1ll << 31)) { *why = "x spans more than 2^31 elements"; return false; }
     if ((q.x_stride_n | q.x_stride_h | q.x_stride_w | q.y_stride_n | q.y_stride_h | q.y_stride_w) & 7) {
       *why = "x / y strides not multiples of 8 elements";
       return false;
@@ -494,7 +564,7 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   args.pad_ = 0;
   // pipeline depth: as many stages as fit while leaving L1 some room for the gather's corner reuse
   int stages = MAX_STAGES, smem_bytes = 0;
-  int budget = m_tiles == 2 ? 164 * 1024 : 132 * 1024;
+  int budget = m_tiles == 2 ? 172 * 1024 : 132 * 1024;
   if (const char* e = getenv("STM_DCN_SMEM_KB")) {          // tuning knob (profiling runs)
     const int v = atoi(e);
     if (v >= 64 && v <= 227) budget = v * 1024;
@@ -524,16 +594,25 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return STM_ERR_CUDA; }
 
   const dim3 grid((unsigned)blocks, (unsigned)n_tiles);
-#ifdef STM_DCN_EXPERIMENTS
-  if (const char* e = getenv("STM_DCN_DBG")) {          // bring-up experiments only (wrong results by design)
-    const int v = atoi(e);
-    if (m_tiles == 2 && v == 1) return launch_t<2, 1>(args, tmap, grid, smem_bytes, stream);
-    if (m_tiles == 2 && v == 2) return launch_t<2, 2>(args, tmap, grid, smem_bytes, stream);
-    if (m_tiles == 2 && v == 3) return launch_t<2, 3>(args, tmap, grid, smem_bytes, stream);
+  // tuning knobs (profiling runs): producer warps and where the generic->async proxy fence is executed
+  const int pw = env_int("STM_DCN_PW", 16);
+  const int depth = env_int("STM_DCN_DEPTH", 2);
+  const bool cfence = env_int("STM_DCN_CFENCE", 1) != 0;
+#define STM_LAUNCH(MT, PW_, D_) \
+  return cfence ? launch_t<MT, PW_, D_, true>(args, tmap, grid, smem_bytes, stream) : launch_t<MT, PW_, D_, false>(args, tmap, grid, smem_bytes, stream)
+  if (m_tiles == 2) {
+    if (pw == 8) {                // 8 gather tasks per thread per K block
+      if (depth >= 4) { STM_LAUNCH(2, 8, 4); }
+      STM_LAUNCH(2, 8, 2);
+    }
+    STM_LAUNCH(2, 16, 2);
   }
-#endif
-  if (m_tiles == 2) return launch_t<2>(args, tmap, grid, smem_bytes, stream);
-  return launch_t<1>(args, tmap, grid, smem_bytes, stream);
+  if (pw == 8) {                  // 4 tasks
+    if (depth >= 4) { STM_LAUNCH(1, 8, 4); }
+    STM_LAUNCH(1, 8, 2);
+  }
+  STM_LAUNCH(1, 16, 2);           // 2 tasks
+#undef STM_LAUNCH
 }
 
 }  // namespace stm

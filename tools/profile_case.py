@@ -18,6 +18,7 @@ ap.add_argument("case")
 ap.add_argument("--frames", type=int, default=72)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--backend", default="auto")
+ap.add_argument("--offset-scale", type=float, default=2.0)
 a = ap.parse_args()
 dev = "cuda"
 torch.manual_seed(0)
@@ -56,7 +57,7 @@ if a.case.startswith("fcb"):
     wp = ops.pack_weight(w, spec, torch.bfloat16)
     lv = fpn_level_sizes()
     xs = [torch.randn(F, 256, h, ww, device=dev).bfloat16().contiguous(memory_format=torch.channels_last) for h, ww in lv]
-    offs = [torch.randn(F, 2 * kh * kw, h, ww, device=dev) * 2 for h, ww in lv]
+    offs = [torch.randn(F, 2 * kh * kw, h, ww, device=dev) * a.offset_scale for h, ww in lv]
     outs = ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=a.backend)
     px = sum(h * ww for h, ww in lv)
     timeit(lambda: ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=a.backend, outs=outs),
@@ -69,7 +70,7 @@ elif a.case.startswith("bb"):
     w = (torch.randn(C, C, 3, 3, device=dev) / (C * 9) ** 0.5).bfloat16()
     wp = ops.pack_weight(w, spec, torch.bfloat16)
     x = torch.randn(F, C, H, W, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
-    om = torch.randn(F, 27, Ho, Wo, device=dev).bfloat16()
+    om = (torch.randn(F, 27, Ho, Wo, device=dev) * (a.offset_scale / 2.0)).bfloat16()
     bias = torch.randn(C, device=dev)
     outs = ops.deform_conv2d_multi([x], [om[:, :18]], [om[:, 18:]], wp, bias, spec, mask_sigmoid=True, backend=a.backend)
     timeit(lambda: ops.deform_conv2d_multi([x], [om[:, :18]], [om[:, 18:]], wp, bias, spec, mask_sigmoid=True, backend=a.backend, outs=outs),
