@@ -72,6 +72,23 @@ class HotPathConfig:
         return f"{'R101' if self.backbone == 'r101' else 'R50'}-DCN-FPN " + "+".join(parts)
 
 
+class StreamedIO:
+    """Streams and device staging buffers of `HotPath.forward_streamed` (allocated once, reused every step)."""
+
+    def __init__(self, device, chunk_frames: int = 12):
+        self.device = device
+        self.chunk_frames = chunk_frames
+        self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(device) for _ in range(3))
+        self._d_in: Dict[str, torch.Tensor] = {}
+
+    def device_inputs(self, host_in: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        for k, v in host_in.items():
+            t = self._d_in.get(k)
+            if t is None or t.shape != v.shape or t.dtype != v.dtype:
+                self._d_in[k] = torch.empty_like(v, device=self.device)      # keeps the channels-last strides
+        return self._d_in
+
+
 class HotPath(torch.nn.Module):
     """Holds the hot path's weights (random, seeded; offset predictors NON-zero) and runs it."""
 
@@ -169,6 +186,82 @@ class HotPath(torch.nn.Module):
                 if fpn_next.shape[0] > 0:
                     out["tf.concat"] = self.temporal_fusion(fpn_ref, fpn_next, t2s_ref, t2s_next)
         return out
+
+    # ---------------------------------------------------------------- end to end from host memory
+    @torch.no_grad()
+    def forward_streamed(self, host_in: Dict[str, torch.Tensor], host_out: Dict[str, torch.Tensor], io: "StreamedIO",
+                         plan: Optional[sharding.ShardPlan] = None, rank: int = 0, group=None) -> None:
+        """The same step as `forward`, fed from PINNED HOST tensors and delivering every result into pinned
+        host tensors (`host_out`, keyed like `forward`'s result; one `tf.concat` per call).  The frame batch
+        is cut into chunks; host->device copies, kernels and device->host copies of consecutive chunks run
+        on three streams, so the PCIe transfers in both directions overlap each other and the compute.
+        Temporal fusion goes first (its inputs are small and every later chunk is independent of it)."""
+        n = next(iter(host_in.values())).shape[0]
+        d_in = io.device_inputs(host_in)
+        keep = []                                            # results stay referenced until the final sync
+
+        def h2d(keys, a, b, ev):
+            with torch.cuda.stream(io.s_in):
+                for k in keys:
+                    d_in[k][a:b].copy_(host_in[k][a:b], non_blocking=True)
+                ev.record(io.s_in)
+
+        def d2h(pairs, ev):
+            with torch.cuda.stream(io.s_out):
+                io.s_out.wait_event(ev)
+                for dst, src in pairs:
+                    src.record_stream(io.s_out)
+                    dst.copy_(src, non_blocking=True)
+
+        tf_keys = [k for k in host_in if k.startswith("tf.")]
+        frame_keys = [k for k in host_in if not k.startswith("tf.")]
+        if tf_keys:
+            ev_in, ev_done = torch.cuda.Event(), torch.cuda.Event()
+            h2d(tf_keys, 0, n, ev_in)
+            with torch.cuda.stream(io.s_comp):
+                io.s_comp.wait_event(ev_in)
+                sub = self._tf_only({k: d_in[k] for k in tf_keys}, plan, rank, group)
+                ev_done.record(io.s_comp)
+            keep.append(sub)
+            d2h([(host_out[k], v) for k, v in sub.items()], ev_done)
+        for a in range(0, n, io.chunk_frames):
+            b = min(n, a + io.chunk_frames)
+            ev_in, ev_done = torch.cuda.Event(), torch.cuda.Event()
+            h2d(frame_keys, a, b, ev_in)
+            with torch.cuda.stream(io.s_comp):
+                io.s_comp.wait_event(ev_in)
+                sub = self._frames_only({k: d_in[k][a:b] for k in frame_keys})
+                ev_done.record(io.s_comp)
+            keep.append(sub)
+            d2h([(host_out[k][a:b], v) for k, v in sub.items()], ev_done)
+        io.s_out.synchronize()
+        io.s_comp.synchronize()
+
+    def _frames_only(self, inp):
+        """Backbone DCN + FCB of a batch of frames (per-frame independent operators)."""
+        out = {}
+        for i, m in enumerate(self.backbone_dcn):
+            out[f"dcn{i}.y"] = m(inp[f"dcn{i}.x"])
+        for k, m in enumerate(self.fcb):
+            xs = [inp[f"fcb.x{l}"] for l in range(len(self.level_sizes))]
+            boxes = [inp[f"fcb.box{l}.{k}"] for l in range(len(self.level_sizes))]
+            for l, y in enumerate(m.calibrate_levels(xs, boxes)):
+                out[f"fcb.y{l}.{k}"] = y
+        return out
+
+    def _tf_only(self, inp, plan, rank, group):
+        """Temporal fusion of every local frame pair (halo exchange included); ONE [pairs, 633, H, W] result."""
+        n = inp["tf.fpn"].shape[0]
+        if plan is None:
+            plan = sharding.make_plan(1, n, 1, "clip")
+        halo = None
+        if plan.world_size > 1:
+            halo = sharding.exchange_halo(plan, rank, [inp["tf.fpn"], inp["tf.t2s"]], group)
+        fpn_ref, fpn_next = sharding.temporal_pairs(plan, rank, inp["tf.fpn"], halo[0] if halo else None)
+        t2s_ref, t2s_next = sharding.temporal_pairs(plan, rank, inp["tf.t2s"], halo[1] if halo else None)
+        if fpn_next.shape[0] == 0:
+            return {}
+        return {"tf.concat": self.temporal_fusion(fpn_ref, fpn_next, t2s_ref, t2s_next)}
 
     def temporal_fusion(self, fpn_ref, fpn_next, t2s_ref, t2s_next):
         from .temporal_fusion import correlate_concat

@@ -374,3 +374,28 @@ def test_error_conventions(cuda_device):
     assert ops.deform_conv2d(xb, torch.zeros(36, 18, 5, 5, device=cuda_device), w, padding=1).shape == (36, 8, 5, 5)
     # empty batch
     assert ops.deform_conv2d(x[:0], torch.zeros(0, 18, 5, 5, device=cuda_device), w, padding=1).shape == (0, 8, 5, 5)
+
+
+# ------------------------------------------------------------------------------------------
+# the hot path end to end from host memory == the device-resident step, bit for bit
+# ------------------------------------------------------------------------------------------
+def test_forward_streamed_equals_resident_step(cuda_device):
+    from stmask_b200 import sharding
+    from stmask_b200.hotpath import HotPath, HotPathConfig, StreamedIO
+    cfg = HotPathConfig(backbone="r50", fcb="ada", height=96, width=160)
+    hp = HotPath(cfg, cuda_device, seed=0)
+    n = 10
+    plan = sharding.make_plan(2, 5, 1, "clip")                 # two 5-frame clips: pairs must not cross the clip boundary
+    host_in = hp.make_inputs(n, cuda_device, seed=3, pinned_host=True)
+    d_in = {k: v.to(cuda_device) for k, v in host_in.items()}
+    want = dict(hp._frames_only({k: v for k, v in d_in.items() if not k.startswith("tf.")}))
+    want.update(hp._tf_only({k: v for k, v in d_in.items() if k.startswith("tf.")}, plan, 0, None))
+    whole = hp(d_in, plan, 0)                                  # the schedulable unit bench.py times
+    tf_whole = whole["tf.concat"] if not isinstance(whole["tf.concat"], list) else torch.cat(whole["tf.concat"], 0)
+    assert want["tf.concat"].shape[0] == 8 and torch.equal(want["tf.concat"], tf_whole)
+    host_out = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in want.items()}
+    io = StreamedIO(cuda_device, chunk_frames=4)               # 4 + 4 + 2 frames
+    for _ in range(2):                                         # second pass reuses the staging buffers
+        hp.forward_streamed(host_in, host_out, io, plan, 0)
+    for k, v in want.items():
+        assert torch.equal(host_out[k], v.cpu()), k
