@@ -40,46 +40,86 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region, polled through NVML every few ms (the timed
+    region is tens of ms long; nvidia-smi's loop is too coarse for it).  Falls back to `nvidia-smi -lms`."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, period_s: float = 0.002):
+        self.index, self.period = index, period_s
+        self.sm, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self.stop = threading.Event()
+        self.thread = self.proc = None
+        self.src = "nvml"
+
+    def _nvml_loop(self, nv, h):
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else nv.nvmlClocksThrottleReasonHwSlowdown),
+                 ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", None) or nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", None) or nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                 ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", None) or nv.nvmlClocksThrottleReasonSwPowerCap))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = get_reasons(h)
+                for n, bit in names:
+                    if r & bit:
+                        self.reasons.add(n)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+            except Exception:
+                pass
+            self.stop.wait(self.period)
+
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            if len(r) >= 9 and r[1].replace(".", "").isdigit():
+                self.sm.append(float(r[1]))
+                self.max_mhz = float(r[2])
+                for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES through the PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id
+            dom = torch.cuda.get_device_properties(self.index).pci_domain_id
+            dev_id = torch.cuda.get_device_properties(self.index).pci_device_id
+            h = nv.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev_id:02x}.0")
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.src = "nvidia-smi"
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                              "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+                self.thread.start()
+            except OSError:
+                self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
+        self.stop.set()
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.05)
             self.proc.terminate()
-            self.t.join(timeout=2)
+        if self.thread:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        if not sm:
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        reasons = set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][2]), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.src}
+        if self.power:
+            out["power_w_max"] = max(self.power)
+        return out
 
 
 # ----------------------------------------------------------------------------------------------

@@ -43,7 +43,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define STM_ABI_VERSION 1
+#define STM_ABI_VERSION 2
 
 typedef enum StmStatus {
   STM_OK = 0,
@@ -177,6 +177,12 @@ typedef struct StmCorrDesc {
   int32_t feat_dtype;
   int64_t feat_a_stride_n, feat_a_stride_h, feat_a_stride_w;
   int64_t feat_b_stride_n, feat_b_stride_h, feat_b_stride_w;
+  /* STM_CORR_COPY_FEATS only: channel at which feat_a starts; 0 means P*P (the reference's 633-channel
+   * concat).  A larger value pads the correlation block — channels [P*P, feat_c_offset) are written as
+   * zeros — e.g. 128 for P = 11, which makes every block of a channels-last bf16 pixel row 16-byte aligned
+   * (the layout the fused temporal-fusion path uses: [corr 121 | 0 x 7 | T2S_ref 256 | T2S_next 256]). */
+  int32_t feat_c_offset;
+  int32_t reserved_;
 } StmCorrDesc;
 
 /* out[b,ph,pw,y,x] = post( scale * sum_c x1[b,y,x,c] * x2[b, y+(ph-r)d, x+(pw-r)d, c] ), zero outside x2. */

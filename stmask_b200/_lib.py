@@ -19,7 +19,7 @@ BACKEND_NAMES = {BACKEND_AUTO: "auto", BACKEND_SIMT: "simt", BACKEND_TCGEN05: "t
 DCN_RELU, DCN_MASK_SIGMOID, DCN_ZERO_OFFSET = 1, 2, 4
 CORR_LEAKY_RELU, CORR_RELU, CORR_COPY_FEATS = 1, 2, 4
 DCN_MAX_PROBLEMS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class StmError(RuntimeError):
@@ -55,6 +55,7 @@ class StmCorrDesc(C.Structure):
         ("feat_c", C.c_int32), ("feat_dtype", C.c_int32),
         ("feat_a_stride_n", C.c_int64), ("feat_a_stride_h", C.c_int64), ("feat_a_stride_w", C.c_int64),
         ("feat_b_stride_n", C.c_int64), ("feat_b_stride_h", C.c_int64), ("feat_b_stride_w", C.c_int64),
+        ("feat_c_offset", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

@@ -118,6 +118,8 @@ static int validate_corr(const StmCorrDesc* d, const void* x1, const void* x2, c
   if (d->flags & STM_CORR_COPY_FEATS) {
     STM_CHECK_ARG(fa && fb && d->feat_c > 0 && dtype_ok(d->feat_dtype), "COPY_FEATS needs feat_a/feat_b/feat_c");
     STM_CHECK_ARG(d->feat_a_stride_w >= d->feat_c && d->feat_b_stride_w >= d->feat_c, "feat pixel stride smaller than feat_c");
+    STM_CHECK_ARG(d->feat_c_offset == 0 || d->feat_c_offset >= d->patch * d->patch,
+                  "feat_c_offset %d overlaps the %d correlation channels", d->feat_c_offset, d->patch * d->patch);
   }
   return STM_OK;
 }

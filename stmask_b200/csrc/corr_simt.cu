@@ -132,11 +132,13 @@ corr_simt_kernel(const StmCorrDesc d, const T* __restrict__ x1, const T* __restr
     const bool relu = (d.flags & STM_CORR_RELU) != 0;
     const FT* pa = fa + b * d.feat_a_stride_n + y * d.feat_a_stride_h + x * d.feat_a_stride_w;
     const FT* pb = fb + b * d.feat_b_stride_n + y * d.feat_b_stride_h + x * d.feat_b_stride_w;
+    const int foff = d.feat_c_offset > 0 ? d.feat_c_offset : PP;
+    for (int c = PP + lane; c < foff; c += 32) out[obase + (int64_t)c * d.out_stride_c] = from_f32<OT>(0.f);   // pad channels
     for (int c = lane; c < d.feat_c; c += 32) {
       float va = to_f32(pa[c]), vb = to_f32(pb[c]);
       if (relu) { va = fmaxf(va, 0.f); vb = fmaxf(vb, 0.f); }
-      out[obase + (int64_t)(PP + c) * d.out_stride_c] = from_f32<OT>(va);
-      out[obase + (int64_t)(PP + d.feat_c + c) * d.out_stride_c] = from_f32<OT>(vb);
+      out[obase + (int64_t)(foff + c) * d.out_stride_c] = from_f32<OT>(va);
+      out[obase + (int64_t)(foff + d.feat_c + c) * d.out_stride_c] = from_f32<OT>(vb);
     }
   }
 }

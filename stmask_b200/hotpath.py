@@ -265,7 +265,7 @@ class HotPath(torch.nn.Module):
 
     def temporal_fusion(self, fpn_ref, fpn_next, t2s_ref, t2s_next):
         from .temporal_fusion import correlate_concat
-        return correlate_concat(fpn_ref, fpn_next, t2s_ref, t2s_next, CORR_PATCH, 1, channels_last=True)
+        return correlate_concat(fpn_ref, fpn_next, t2s_ref, t2s_next, CORR_PATCH, 1, channels_last=True, padded=True)
 
     # ---------------------------------------------------------------- accounting
     def flops_per_frame(self) -> Dict[str, float]:

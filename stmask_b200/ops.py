@@ -362,8 +362,12 @@ def fcb_ada_offsets(shape: torch.Tensor, weight: torch.Tensor, dtype: Optional[t
 def correlation(x1: torch.Tensor, x2: torch.Tensor, patch_size: int = 11, dilation_patch: int = 1, *,
                 scale: float = 1.0, leaky_slope: Optional[float] = None, relu: bool = False,
                 feats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, out_dtype: Optional[torch.dtype] = None,
-                channels_last: bool = False, backend: str = "auto") -> torch.Tensor:
+                channels_last: bool = False, backend: str = "auto", feat_channel_offset: Optional[int] = None) -> torch.Tensor:
     """Cost volume [B, P*P, H, W] (+ 2*feat_c concat channels when `feats` is given).
+
+    `feat_channel_offset` (with `feats`): channel at which the first feature map starts (default P*P, the
+    reference's concat).  A larger value pads the correlation block with zero channels; 128 for P = 11 makes
+    every block of a channels-last bf16 pixel row 16-byte aligned, which is what the fast epilogue needs.
 
     out[b, ph*P+pw, y, x] = post(scale * <x1[b,:,y,x], x2[b,:,y+(ph-r)d, x+(pw-r)d]>), zero outside x2.
     `channels_last=True` returns NHWC memory (what the RoIAlign/TemporalNet convs want);
@@ -401,7 +405,12 @@ def correlation(x1: torch.Tensor, x2: torch.Tensor, patch_size: int = 11, dilati
         fdt = _dt(fa, "feats")
         flags |= L.CORR_COPY_FEATS
     odt = out_dtype or x1.dtype
-    ch = P * P + 2 * fc
+    foff = P * P
+    if feat_channel_offset is not None:
+        if feats is None or int(feat_channel_offset) < P * P:
+            raise ValueError("feat_channel_offset needs feats and must be >= patch_size**2")
+        foff = int(feat_channel_offset)
+    ch = foff + 2 * fc
     out = torch.empty((b, ch, h, w), dtype=odt, device=x1.device,
                       memory_format=torch.channels_last if channels_last else torch.contiguous_format)
     if out.numel() == 0:
@@ -416,6 +425,7 @@ def correlation(x1: torch.Tensor, x2: torch.Tensor, patch_size: int = 11, dilati
     desc.x2_stride_n, desc.x2_stride_h, desc.x2_stride_w = bb.stride(0), bb.stride(2), bb.stride(3)
     desc.out_stride_n, desc.out_stride_c, desc.out_stride_h, desc.out_stride_w = out.stride()
     desc.feat_c, desc.feat_dtype = fc, fdt
+    desc.feat_c_offset = foff if feats is not None else 0
     if fa is not None:
         desc.feat_a_stride_n, desc.feat_a_stride_h, desc.feat_a_stride_w = fa.stride(0), fa.stride(2), fa.stride(3)
         desc.feat_b_stride_n, desc.feat_b_stride_h, desc.feat_b_stride_w = fb.stride(0), fb.stride(2), fb.stride(3)

@@ -302,6 +302,31 @@ def test_correlate_golden_reference_call_site(cuda_device, dtype):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("backend", ["simt", "auto"])
+@pytest.mark.parametrize("shape,P", [((3, 256, 24, 40), 11), ((2, 256, 23, 37), 11), ((2, 128, 12, 20), 5), ((1, 64, 3, 5), 11)])
+def test_correlate_concat_padded_layout(cuda_device, dtype, backend, shape, P):
+    """The B200 concat layout [corr P*P | zeros | T2S_ref | T2S_next] (16-byte aligned blocks, the fast epilogue
+    of the tcgen05 kernel) against the oracle's reference-order concat; pad channels must be exactly zero."""
+    from stmask_b200.temporal_fusion import padded_corr_channels, unpad_concat
+    ops = _ops()
+    rng = np.random.default_rng(shape[2] * 7 + P)
+    x1, x2 = q(rng.standard_normal(shape), dtype), q(rng.standard_normal(shape), dtype)
+    fshape = (shape[0], 256, shape[2], shape[3])
+    ta, tb = q(rng.standard_normal(fshape), dtype), q(rng.standard_normal(fshape), dtype)
+    cp = padded_corr_channels(P)
+    got = ops.correlation(dev(x1, dtype, cuda_device, True), dev(x2, dtype, cuda_device, True), P, 1, scale=1.0 / shape[1], relu=True,
+                          feats=(dev(ta, dtype, cuda_device, True), dev(tb, dtype, cuda_device, True)), channels_last=True,
+                          feat_channel_offset=cp, backend=backend)
+    assert got.shape == (shape[0], cp + 512, shape[2], shape[3]) and got.stride(1) == 1
+    assert (got[:, P * P:cp] == 0).all()
+    want = np.maximum(np.concatenate([oracle.correlate(x1, x2, P, 1), ta, tb], 1), 0)    # relu(leaky(v)) == relu(v)
+    assert rel_err(unpad_concat(got, P).float().cpu().numpy(), want) <= TOL[dtype]
+    # the feature blocks are pure copies (+ReLU): bit exact
+    assert torch.equal(got[:, cp:cp + 256].float().cpu(), torch.from_numpy(np.maximum(ta, 0)))
+    assert torch.equal(got[:, cp + 256:].float().cpu(), torch.from_numpy(np.maximum(tb, 0)))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("backend", ["simt", "auto"])
 @pytest.mark.parametrize("shape,P,d", [((2, 256, 24, 40), 11, 1), ((2, 256, 24, 40), 11, 2), ((1, 256, 48, 80), 11, 1),
                                        ((3, 256, 3, 5), 11, 1), ((2, 256, 6, 10), 11, 2), ((2, 256, 23, 40), 11, 1),
                                        ((2, 64, 12, 20), 5, 1), ((1, 40, 7, 9), 3, 3), ((1, 13, 6, 7), 7, 1),
@@ -398,4 +423,8 @@ def test_forward_streamed_equals_resident_step(cuda_device):
     for _ in range(2):                                         # second pass reuses the staging buffers
         hp.forward_streamed(host_in, host_out, io, plan, 0)
     for k, v in want.items():
-        assert torch.equal(host_out[k], v.cpu()), k
+        if k.startswith("dcn"):
+            # the offset/mask predictor is a cuDNN conv whose algorithm may change with the batch size of a chunk
+            assert rel_err(host_out[k].float().numpy(), v.float().cpu().numpy()) <= 2e-2, k
+        else:
+            assert torch.equal(host_out[k], v.cpu()), k

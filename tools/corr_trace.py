@@ -1,27 +1,31 @@
-"""Per-phase clock64 trace of the tcgen05 correlation kernel (first tile of every CTA)."""
+"""Per-phase globaltimer trace (ns) of the tcgen05 correlation kernel: first 4 tiles of every CTA.
+    python tools/corr_trace.py [pairs]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from stmask_b200 import ops
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 71
-fused = (sys.argv[2] != "plain") if len(sys.argv) > 2 else True
 x1 = torch.randn(n, 256, 24, 40, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
 x2, t1, t2 = torch.randn_like(x1), torch.randn_like(x1), torch.randn_like(x1)
-buf = torch.zeros(148 * 32, dtype=torch.int64, device="cuda")
-def run():
-    if fused:
-        return ops.correlation(x1, x2, 11, 1, scale=1 / 256, relu=True, feats=(t1, t2), channels_last=True)
-    return ops.correlation(x1, x2, 11, 1, channels_last=False)
+buf = torch.zeros(148 * 64, dtype=torch.int64, device="cuda")
+run = lambda: ops.correlation(x1, x2, 11, 1, scale=1 / 256, relu=True, feats=(t1, t2), channels_last=True, feat_channel_offset=128)
 run(); torch.cuda.synchronize()
 os.environ["STM_DEBUG_BUF"] = hex(buf.data_ptr())
 run(); torch.cuda.synchronize()
-t = buf.view(148, 32).cpu()
-names = {1: "tma c0 issued", 2: "tma c1 issued", 3: "tma c2 issued", 4: "tma c3 issued", 5: "mma sees c0", 6: "mma sees c1", 7: "mma sees c2",
-         8: "mma sees c3", 9: "mma committed tile", 10: "epi sees tmem_full", 11: "phase1 done", 12: "phase2/3 done (tile 0)", 13: "tile 1 done", 14: "teardown"}
+t = buf.view(148, 64).cpu()
+t0 = int(t[:, 59].min())
+ev = ["tma first", "tma last", "mma first full", "mma last full", "epi start", "phase0 done", "tmem_full seen", "phase1 done", "phase2 done"]
 for cta in (0, 73, 147):
-    base = int(t[cta, 0])
-    print(f"CTA {cta}:", ", ".join(f"{names[i]}={int(t[cta, i]) - base}" for i in range(1, 15) if int(t[cta, i]) > 0))
-d = (t[:, 1:15] - t[:, :1]).float()
-d[t[:, 1:15] == 0] = float("nan")
-print("median over CTAs:", {names[i + 1]: float(torch.nanmedian(d[:, i])) for i in range(14)})
+    print(f"CTA {cta}: body start +{int(t[cta, 59]) - t0} ns, teardown +{int(t[cta, 58]) - t0} ns")
+    for k in range(4):
+        row = [int(t[cta, k * 12 + e]) for e in range(9)]
+        if row[4] == 0:
+            continue
+        print(f"   tile {k}: " + ", ".join(f"{ev[e]}={row[e] - t0}" for e in range(9)))
+d = t.clone().float()
+d[t == 0] = float("nan")
+print("median over CTAs (ns from first body start):")
+for k in range(4):
+    print(f"   tile {k}: " + ", ".join(f"{ev[e]}={float(torch.nanmedian(d[:, k * 12 + e])) - t0:.0f}" for e in range(9)))
+print(f"   teardown median {float(torch.nanmedian(d[:, 58])) - t0:.0f} max {float(d[:, 58].max()) - t0:.0f}")

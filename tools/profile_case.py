@@ -80,7 +80,10 @@ elif a.case == "corr":
     x1 = torch.randn(n, 256, 24, 40, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
     x2 = torch.randn_like(x1)
     t1, t2 = torch.randn_like(x1), torch.randn_like(x1)
-    fn = lambda: ops.correlation(x1, x2, 11, 1, scale=1 / 256, relu=True, feats=(t1, t2), channels_last=True, backend=a.backend)
+    foff = None if os.environ.get("STM_CORR_UNPADDED") else 128
+    fn = lambda: ops.correlation(x1, x2, 11, 1, scale=1 / 256, relu=True, feats=(t1, t2), channels_last=True, backend=a.backend,
+                                 feat_channel_offset=foff)
+    print("algorithmic (SURVEY 8d) GB/s = reported x", (633 + 512) / (633 + 1024.0))
     timeit(fn, nbytes=n * 960 * (633 + 2 * 256 + 2 * 256) * 2.0)
 elif a.case == "corrsweep":       # BASELINE.json configs[1]: batch 8 over P3..P7, plain cost volume
     lv = fpn_level_sizes()
