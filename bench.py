@@ -30,6 +30,15 @@ FRAMES_PER_CLIP = 36
 METRIC = "frames/sec @360x640 R101 FCA+FCB+TF"
 
 
+def _traffic(key, count_key, count):
+    """Measured DRAM bytes per launch of the dominant kernels (one ncu --set full capture each, profiles/)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]
+        return t["bytes"] if t[count_key] == count else None
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -338,7 +347,7 @@ def main():
         be = ops.deform_conv2d_backend(tuple(xs[0].shape), spec, xs[0].dtype, args.backend)
         roof = {"kernel": f"deform_conv2d[{be}] FCB 3x5 256->256, P3..P7, {n_local} frames, one launch", "bound": "tensor",
                 "achieved": ach, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_burst"],
-                "traffic": None, "ms_per_launch": k_ms, "flops_per_launch": flops,
+                "traffic": _traffic("dcn_fcb35", "frames", n_local), "ms_per_launch": k_ms, "flops_per_launch": flops,
                 "peak_source": peaks["src"] + ", burst (kernel timed alone)"}
     if hp_cfg.temporal_fusion:
         fr, fn = sharding.temporal_pairs(sharding.make_plan(1, n_local, 1), 0, inp["tf.fpn"], None)
@@ -355,13 +364,14 @@ def main():
         es = 2 if hp_cfg.dtype == torch.bfloat16 else 4
         npx = fr.shape[0] * fr.shape[2] * fr.shape[3]
         # H*W*(2C + P^2) bytes, plus the 2*Ct WRITTEN concat bytes because this kernel copies them;
-        # the 2*Ct feature bytes it also has to READ are reported separately (achieved_incl_feature_reads)
+        # the 2*Ct feature bytes it also has to READ are reported separately (achieved_incl_feature_reads); the 7 zero
+        # pad channels of the padded layout are written but not counted
         nbytes = npx * (2 * 256 + 121 + 2 * 256) * es
         nbytes_all = nbytes + npx * 2 * 256 * es
         ach = nbytes / (k_ms / 1e3) / 1e9
         corr_roof = {"kernel": f"correlation+concat[{ops.correlation_backend(tuple(fr.shape), fr.dtype, 11, 1, args.backend)}] "
                                f"P=11 C=256 24x40, {fr.shape[0]} frame pairs, one launch", "bound": "hbm", "achieved": ach,
-                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms_per_launch": k_ms,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": _traffic("corr_fused", "pairs", int(fr.shape[0])), "ms_per_launch": k_ms,
                      "bytes_per_launch": nbytes, "achieved_incl_feature_reads": nbytes_all / (k_ms / 1e3) / 1e9,
                      "peak_source": peaks["src"]}
 
