@@ -39,6 +39,22 @@ def _traffic(key, count_key, count):
         return None
 
 
+def _time_launches(fn, n):
+    """Average device time of one launch: n launches queued back to back between ONE pair of CUDA events on the
+    launching (current) stream, so host launch latency is not part of a sub-100-us kernel's figure.  The
+    operands of consecutive launches (> 126 MB read + written) do not fit L2."""
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -333,14 +349,7 @@ def main():
         spec = m.conv_adaption.spec()
         wp = m.conv_adaption._cache.weight(m.conv_adaption.weight, spec, xs[0].dtype)
         outs = ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=args.backend)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        torch.cuda.synchronize()
-        for a, b in evs:
-            a.record()
-            ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=args.backend, outs=outs)
-            b.record()
-        torch.cuda.synchronize()
-        k_ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        k_ms = _time_launches(lambda: ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=args.backend, outs=outs), reps)
         px = sum(h * w for h, w in hp.level_sizes)
         flops = 2.0 * n_local * px * 256 * 256 * 15
         ach = flops / (k_ms / 1e3) / 1e12
@@ -352,15 +361,7 @@ def main():
     if hp_cfg.temporal_fusion:
         fr, fn = sharding.temporal_pairs(sharding.make_plan(1, n_local, 1), 0, inp["tf.fpn"], None)
         tr, tn = sharding.temporal_pairs(sharding.make_plan(1, n_local, 1), 0, inp["tf.t2s"], None)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        hp.temporal_fusion(fr, fn, tr, tn)
-        torch.cuda.synchronize()
-        for a, b in evs:
-            a.record()
-            hp.temporal_fusion(fr, fn, tr, tn)
-            b.record()
-        torch.cuda.synchronize()
-        k_ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        k_ms = _time_launches(lambda: hp.temporal_fusion(fr, fn, tr, tn), 4 * reps)
         es = 2 if hp_cfg.dtype == torch.bfloat16 else 4
         npx = fr.shape[0] * fr.shape[2] * fr.shape[3]
         # H*W*(2C + P^2) bytes, plus the 2*Ct WRITTEN concat bytes because this kernel copies them;

@@ -99,7 +99,7 @@ __device__ __forceinline__ uint64_t add_wide(uint32_t lo, uint32_t hi, uint32_t 
 // thread before its release): a producer-side fence.proxy.async compiles to MEMBAR.ALL.CTA, which also
 // waits for the gather loads that are already in flight for the NEXT K block and drains the pipeline.
 template <int M_TILES, int PW, int D, bool CFENCE>
-__global__ void __launch_bounds__(PW * 32 + 64, 1)
+__global__ void __launch_bounds__(PW * 32 + 64, (M_TILES == 1 && PW == 8) ? 2 : 1)
 dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap tmap_w) {
   constexpr int ROWS = TILE_M * M_TILES;
   constexpr int PT = PW * 32;                           // producer threads
@@ -545,9 +545,15 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   // backbone layers); fall back to 128-row CTAs only when 256-row CTAs could not even half-fill the GPU
   const int64_t ctas256 = ((rows + 255) / 256) * n_tiles;
   int m_tiles = (ctas256 >= sm_count() / 2 && 2 * block_n <= 512) ? 2 : 1;
+  // N <= 128 (the C = 128 backbone stage): the MMA is cheap, the gather and the per-CTA prologue / epilogue
+  // dominate.  Two 128-row CTAs with 8 producer warps each share an SM (registers, 128 TMEM columns and
+  // < 113 KB shared memory each), so one CTA's prologue / epilogue hides behind the other's main loop
+  // (B200: 0.358 -> 0.323 ms on the 48x80 C=128 layers).  With N = 256 the doubled weight traffic costs more.
+  bool two_ctas = block_n <= 128;
+  if (two_ctas) m_tiles = 1;
   if (const char* e = getenv("STM_DCN_MTILES")) {           // tuning knob (profiling runs)
     const int v = atoi(e);
-    if ((v == 1 || v == 2) && v * block_n <= 512) m_tiles = v;
+    if ((v == 1 || v == 2) && v * block_n <= 512) { m_tiles = v; two_ctas = false; }
   }
   const int rows_per_cta = TILE_M * m_tiles;
   int blocks = 0;
@@ -564,7 +570,7 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   args.pad_ = 0;
   // pipeline depth: as many stages as fit while leaving L1 some room for the gather's corner reuse
   int stages = MAX_STAGES, smem_bytes = 0;
-  int budget = m_tiles == 2 ? 172 * 1024 : 132 * 1024;
+  int budget = m_tiles == 2 ? 172 * 1024 : (two_ctas ? 110 * 1024 : 132 * 1024);
   if (const char* e = getenv("STM_DCN_SMEM_KB")) {          // tuning knob (profiling runs)
     const int v = atoi(e);
     if (v >= 64 && v <= 227) budget = v * 1024;
@@ -595,7 +601,7 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
 
   const dim3 grid((unsigned)blocks, (unsigned)n_tiles);
   // tuning knobs (profiling runs): producer warps and where the generic->async proxy fence is executed
-  const int pw = env_int("STM_DCN_PW", 16);
+  const int pw = env_int("STM_DCN_PW", two_ctas ? 8 : 16);
   const int depth = env_int("STM_DCN_DEPTH", 2);
   const bool cfence = env_int("STM_DCN_CFENCE", 1) != 0;
 #define STM_LAUNCH(MT, PW_, D_) \
