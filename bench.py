@@ -359,9 +359,9 @@ def main():
                 "traffic": _traffic("dcn_fcb35", "frames", n_local), "ms_per_launch": k_ms, "flops_per_launch": flops,
                 "peak_source": peaks["src"] + ", burst (kernel timed alone)"}
     if hp_cfg.temporal_fusion:
-        fr, fn = sharding.temporal_pairs(sharding.make_plan(1, n_local, 1), 0, inp["tf.fpn"], None)
-        tr, tn = sharding.temporal_pairs(sharding.make_plan(1, n_local, 1), 0, inp["tf.t2s"], None)
-        k_ms = _time_launches(lambda: hp.temporal_fusion(fr, fn, tr, tn), 4 * reps)
+        one_clip = sharding.make_plan(1, n_local, 1)           # n_local - 1 pairs, read in place through index arrays
+        fr = inp["tf.fpn"][1:]
+        k_ms = _time_launches(lambda: hp._tf_pairs(inp["tf.fpn"], inp["tf.t2s"], one_clip, 0, None), 4 * reps)
         es = 2 if hp_cfg.dtype == torch.bfloat16 else 4
         npx = fr.shape[0] * fr.shape[2] * fr.shape[3]
         # H*W*(2C + P^2) bytes, plus the 2*Ct WRITTEN concat bytes because this kernel copies them;

@@ -43,7 +43,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define STM_ABI_VERSION 2
+#define STM_ABI_VERSION 3
 
 typedef enum StmStatus {
   STM_OK = 0,
@@ -183,6 +183,20 @@ typedef struct StmCorrDesc {
    * (the layout the fused temporal-fusion path uses: [corr 121 | 0 x 7 | T2S_ref 256 | T2S_next 256]). */
   int32_t feat_c_offset;
   int32_t reserved_;
+  /* Optional pair indexing — temporal fusion straight out of a frame batch (no gathered copies of the
+   * (t-1, t) pairs, STMask.py:289-297 generalised): when x1_index / x2_index are non-NULL DEVICE arrays of
+   * `batch` int32, pair i correlates frame x1_index[i] of x1 with frame x2_index[i] of x2 and, with
+   * STM_CORR_COPY_FEATS, copies feat_a[x1_index[i]] and feat_b[x2_index[i]].  x1 / feat_a hold x1_frames
+   * frames, x2 / feat_b hold x2_frames.  An x1_index value v >= x1_frames selects frame v - x1_frames of the
+   * ALTERNATE tensors x1_alt / feat_a_alt: the one-frame halos received from the neighbour rank.
+   * tcgen05 backend only (STM_ERR_UNSUPPORTED otherwise). */
+  const int32_t* x1_index;
+  const int32_t* x2_index;
+  int32_t x1_frames, x2_frames, alt_frames, reserved2_;
+  const void* x1_alt;
+  const void* feat_a_alt;
+  int64_t x1_alt_stride_n, x1_alt_stride_h, x1_alt_stride_w;
+  int64_t feat_a_alt_stride_n, feat_a_alt_stride_h, feat_a_alt_stride_w;
 } StmCorrDesc;
 
 /* out[b,ph,pw,y,x] = post( scale * sum_c x1[b,y,x,c] * x2[b, y+(ph-r)d, x+(pw-r)d, c] ), zero outside x2. */

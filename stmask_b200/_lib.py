@@ -19,7 +19,7 @@ BACKEND_NAMES = {BACKEND_AUTO: "auto", BACKEND_SIMT: "simt", BACKEND_TCGEN05: "t
 DCN_RELU, DCN_MASK_SIGMOID, DCN_ZERO_OFFSET = 1, 2, 4
 CORR_LEAKY_RELU, CORR_RELU, CORR_COPY_FEATS = 1, 2, 4
 DCN_MAX_PROBLEMS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class StmError(RuntimeError):
@@ -56,6 +56,11 @@ class StmCorrDesc(C.Structure):
         ("feat_a_stride_n", C.c_int64), ("feat_a_stride_h", C.c_int64), ("feat_a_stride_w", C.c_int64),
         ("feat_b_stride_n", C.c_int64), ("feat_b_stride_h", C.c_int64), ("feat_b_stride_w", C.c_int64),
         ("feat_c_offset", C.c_int32), ("reserved_", C.c_int32),
+        ("x1_index", C.c_void_p), ("x2_index", C.c_void_p),
+        ("x1_frames", C.c_int32), ("x2_frames", C.c_int32), ("alt_frames", C.c_int32), ("reserved2_", C.c_int32),
+        ("x1_alt", C.c_void_p), ("feat_a_alt", C.c_void_p),
+        ("x1_alt_stride_n", C.c_int64), ("x1_alt_stride_h", C.c_int64), ("x1_alt_stride_w", C.c_int64),
+        ("feat_a_alt_stride_n", C.c_int64), ("feat_a_alt_stride_h", C.c_int64), ("feat_a_alt_stride_w", C.c_int64),
     ]
 
 

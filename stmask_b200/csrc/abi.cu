@@ -121,6 +121,12 @@ static int validate_corr(const StmCorrDesc* d, const void* x1, const void* x2, c
     STM_CHECK_ARG(d->feat_c_offset == 0 || d->feat_c_offset >= d->patch * d->patch,
                   "feat_c_offset %d overlaps the %d correlation channels", d->feat_c_offset, d->patch * d->patch);
   }
+  if (d->x1_index != nullptr || d->x2_index != nullptr) {
+    STM_CHECK_ARG(d->x1_index != nullptr && d->x2_index != nullptr, "x1_index and x2_index must be given together");
+    STM_CHECK_ARG(d->x1_frames > 0 && d->x2_frames > 0, "pair indexing needs x1_frames / x2_frames");
+    STM_CHECK_ARG(d->alt_frames >= 0 && (d->alt_frames == 0 || d->x1_alt != nullptr), "alt_frames without x1_alt");
+    if ((d->flags & STM_CORR_COPY_FEATS) && d->alt_frames > 0) STM_CHECK_ARG(d->feat_a_alt != nullptr, "alt_frames without feat_a_alt");
+  }
   return STM_OK;
 }
 
@@ -237,6 +243,7 @@ int stm_correlation_fwd(const StmCorrDesc* d, const void* x1, const void* x2, co
   const int be = stm_correlation_backend(d);
   if (be < 0) return be;
   if (be == STM_BACKEND_TCGEN05) return launch_corr_tc(*d, x1, x2, fa, fb, out, (cudaStream_t)stream);
+  if (d->x1_index != nullptr) { set_error("pair-indexed correlation needs the tcgen05 backend"); return STM_ERR_UNSUPPORTED; }
   return launch_corr_simt(*d, x1, x2, fa, fb, out, (cudaStream_t)stream);
 }
 

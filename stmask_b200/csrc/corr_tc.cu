@@ -99,6 +99,23 @@ __device__ __forceinline__ TileCoord decode_tile(const StmCorrDesc& d, int tile,
   return t;
 }
 
+// frames of pair `pair`: b1 indexes x1 / feat_a (or, when alt, x1_alt / feat_a_alt), b2 indexes x2 / feat_b
+struct PairFrames {
+  int b1, b2;
+  bool alt;
+};
+__device__ __forceinline__ PairFrames pair_frames(const StmCorrDesc& d, int pair) {
+  PairFrames f;
+  f.b1 = f.b2 = pair;
+  f.alt = false;
+  if (d.x1_index != nullptr) {
+    f.b1 = __ldg(d.x1_index + pair);
+    f.b2 = __ldg(d.x2_index + pair);
+    if (f.b1 >= d.x1_frames) { f.b1 -= d.x1_frames; f.alt = true; }
+  }
+  return f;
+}
+
 __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
   uint32_t r;
   asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
@@ -109,7 +126,7 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
 template <typename OT, int TW, int POST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUtensorMap tmap_x1,
-               const __grid_constant__ CUtensorMap tmap_x2) {
+               const __grid_constant__ CUtensorMap tmap_x2, const __grid_constant__ CUtensorMap tmap_x1_alt) {
   constexpr int MAX_RW = TW + MAX_P - 1;          // <= 32: one tcgen05.ld.x32 covers a region row
   static_assert(MAX_RW <= 32, "tile too wide");
   extern __shared__ uint8_t smem_raw[];
@@ -171,12 +188,14 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
         const TileCoord t = decode_tile(d, tile, a.tiles_per_image, th, TW);
         const int fy = t.sy + dl * t.y0, fx = t.sx + dl * t.x0;           // full-resolution coords of the patch origin
+        const PairFrames pf = pair_frames(d, t.b);
+        const CUtensorMap* m1 = pf.alt ? &tmap_x1_alt : &tmap_x1;
         for (int c = 0; c < a.chunks; ++c) {
           mbar_wait_relaxed(&empty_bar[s], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], bytes);
           uint8_t* st = smem + s * L.stage_bytes;
-          tma_load_4d(st, &tmap_x1, &full_bar[s], c * 64, fx, fy, t.b);
-          tma_load_4d(st + L.a_bytes, &tmap_x2, &full_bar[s], c * 64, fx - r * dl, fy - r * dl, t.b);
+          tma_load_4d(st, m1, &full_bar[s], c * 64, fx, fy, pf.b1);
+          tma_load_4d(st + L.a_bytes, &tmap_x2, &full_bar[s], c * 64, fx - r * dl, fy - r * dl, pf.b2);
           if (a.l2_prefetch) {
             // the smem ring holds only STAGES chunks: pull the chunk that will be loaded STAGES steps from now into
             // L2 already, so that load does not pay DRAM latency on the MMA's critical path
@@ -185,8 +204,9 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
             if (ptile < a.n_tiles) {
               const TileCoord n = ptile == tile ? t : decode_tile(d, ptile, a.tiles_per_image, th, TW);
               const int ny = n.sy + dl * n.y0, nx = n.sx + dl * n.x0;
-              tma_prefetch_4d(&tmap_x1, pc * 64, nx, ny, n.b);
-              tma_prefetch_4d(&tmap_x2, pc * 64, nx - r * dl, ny - r * dl, n.b);
+              const PairFrames nf = ptile == tile ? pf : pair_frames(d, n.b);
+              tma_prefetch_4d(nf.alt ? &tmap_x1_alt : &tmap_x1, pc * 64, nx, ny, nf.b1);
+              tma_prefetch_4d(&tmap_x2, pc * 64, nx - r * dl, ny - r * dl, nf.b2);
             }
           }
           if (c == 0) STM_TRACE(k, 0);
@@ -244,6 +264,7 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
     for (int tile = blockIdx.x; tile < a.n_tiles && copy_feats; tile += gridDim.x, ++k) {
       const TileCoord t = decode_tile(d, tile, a.tiles_per_image, th, TW);
       const int64_t obase = t.b * d.out_stride_n;
+      const PairFrames pf = pair_frames(d, t.b);
       if (et == 0) STM_TRACE(k, 4);
       // ---- phase 0: concat copy of the two feature maps behind the correlation channels.  It does not
       //      depend on the accumulator, so it runs while the tensor core is still working on this tile. ----
@@ -261,9 +282,13 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
             const int x = t.sx + dl * (t.x0 + seg * SEG);                       // first pixel of the segment
             int nv = y < d.h ? (d.w - x + dl - 1) / dl : 0;                     // valid pixels in it
             nv = nv < 0 ? 0 : (nv > SEG ? SEG : nv);
-            const int64_t fsw = (m ? d.feat_b_stride_w : d.feat_a_stride_w) * dl;
-            const __nv_bfloat16* src = m ? reinterpret_cast<const __nv_bfloat16*>(a.fb) + t.b * d.feat_b_stride_n + y * d.feat_b_stride_h + x * d.feat_b_stride_w
-                                         : reinterpret_cast<const __nv_bfloat16*>(a.fa) + t.b * d.feat_a_stride_n + y * d.feat_a_stride_h + x * d.feat_a_stride_w;
+            const bool alt = m == 0 && pf.alt;
+            const int64_t fsw_ = m ? d.feat_b_stride_w : (alt ? d.feat_a_alt_stride_w : d.feat_a_stride_w);
+            const int64_t fsw = fsw_ * dl;
+            const __nv_bfloat16* src =
+                m ? reinterpret_cast<const __nv_bfloat16*>(a.fb) + pf.b2 * d.feat_b_stride_n + y * d.feat_b_stride_h + x * d.feat_b_stride_w
+                  : (alt ? reinterpret_cast<const __nv_bfloat16*>(d.feat_a_alt) + pf.b1 * d.feat_a_alt_stride_n + y * d.feat_a_alt_stride_h + x * d.feat_a_alt_stride_w
+                         : reinterpret_cast<const __nv_bfloat16*>(a.fa) + pf.b1 * d.feat_a_stride_n + y * d.feat_a_stride_h + x * d.feat_a_stride_w);
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + y * d.out_stride_h + x * d.out_stride_w + foff + m * fc;
             const int64_t osw = d.out_stride_w * dl;
             for (int ch = lane; ch < cpr; ch += 32) {
@@ -296,11 +321,13 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
             const int y = t.sy + dl * (t.y0 + ty), x = t.sx + dl * (t.x0 + tx);
             if (y >= d.h || x >= d.w) continue;
             OT* op = out + obase + y * d.out_stride_h + x * d.out_stride_w;
-            const int64_t ia = t.b * d.feat_a_stride_n + y * d.feat_a_stride_h + x * d.feat_a_stride_w;
-            const int64_t ib = t.b * d.feat_b_stride_n + y * d.feat_b_stride_h + x * d.feat_b_stride_w;
+            const void* fa_ = pf.alt ? d.feat_a_alt : a.fa;
+            const int64_t ia = pf.alt ? pf.b1 * d.feat_a_alt_stride_n + y * d.feat_a_alt_stride_h + x * d.feat_a_alt_stride_w
+                                      : pf.b1 * d.feat_a_stride_n + y * d.feat_a_stride_h + x * d.feat_a_stride_w;
+            const int64_t ib = pf.b2 * d.feat_b_stride_n + y * d.feat_b_stride_h + x * d.feat_b_stride_w;
 #pragma unroll 4
             for (int c = c_begin; c < fc; c += c_step) {
-              op[(int64_t)(foff + c) * d.out_stride_c] = from_f32<OT>(feat(a.fa, ia + c));
+              op[(int64_t)(foff + c) * d.out_stride_c] = from_f32<OT>(feat(fa_, ia + c));
               op[(int64_t)(foff + fc + c) * d.out_stride_c] = from_f32<OT>(feat(a.fb, ib + c));
             }
             for (int c = PP + c_begin; c < foff; c += c_step) op[(int64_t)c * d.out_stride_c] = from_f32<OT>(0.f);
@@ -446,13 +473,14 @@ int sm_count_corr() {
 }
 
 template <typename OT, int TW, int POST>
-int launch_t(const CorrTcArgs& args, const CUtensorMap& m1, const CUtensorMap& m2, int grid, int smem_bytes, cudaStream_t stream) {
+int launch_t(const CorrTcArgs& args, const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& m1a, int grid, int smem_bytes,
+             cudaStream_t stream) {
   static int configured = 0;
   if (configured < smem_bytes) {
     STM_CUDA_OK(cudaFuncSetAttribute(corr_tc_kernel<OT, TW, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = smem_bytes;
   }
-  corr_tc_kernel<OT, TW, POST><<<grid, NUM_THREADS, smem_bytes, stream>>>(args, m1, m2);
+  corr_tc_kernel<OT, TW, POST><<<grid, NUM_THREADS, smem_bytes, stream>>>(args, m1, m2, m1a);
   count_launch();
   STM_CUDA_OK(cudaGetLastError());
   return STM_OK;
@@ -539,27 +567,42 @@ int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const v
               (d.feat_c & 7) == 0 && (args.feat_off & 7) == 0 &&
               ((d.out_stride_n | d.out_stride_h | d.out_stride_w) & 7) == 0 &&
               (((d.feat_a_stride_n | d.feat_a_stride_h | d.feat_a_stride_w | d.feat_b_stride_n | d.feat_b_stride_h | d.feat_b_stride_w) & 7) == 0) &&
-              ((((uintptr_t)fa | (uintptr_t)fb | (uintptr_t)out) & 15) == 0);
+              ((((uintptr_t)fa | (uintptr_t)fb | (uintptr_t)out) & 15) == 0) &&
+              (!(d.x1_index != nullptr && d.alt_frames > 0) ||
+               ((((uintptr_t)d.feat_a_alt) & 15) == 0 && ((d.feat_a_alt_stride_n | d.feat_a_alt_stride_h | d.feat_a_alt_stride_w) & 7) == 0));
   // staging row stride (elements).  fast: feat_off elements + 4 (rows stay 8-byte aligned for LDS.64, and the
   // 2-word skew spreads the band scatter over the banks); generic: an odd number of 32-bit words per pixel
   args.stage_stride = args.fast ? args.feat_off + 4 : (oes == 4 ? (P * P + 2) : ((P * P + 3) & ~1));
   const SmemPlan L(args.n_half, args.stage_stride, oes);
   if (L.total > 227 * 1024) { set_error("tcgen05 correlation: shared memory %d B over the limit", L.total); return STM_ERR_UNSUPPORTED; }
 
-  CUtensorMap m1, m2;
-  int rc = encode_nhwc_map(&m1, x1, d.c, d.w, d.h, d.batch, d.x1_stride_w, d.x1_stride_h, d.batch > 1 ? d.x1_stride_n : (int64_t)d.h * d.x1_stride_h,
+  // frame counts of the tensors behind the maps (pair indexing addresses frames, not pairs)
+  const bool indexed = d.x1_index != nullptr;
+  const int nb1 = indexed ? d.x1_frames : d.batch, nb2 = indexed ? d.x2_frames : d.batch;
+  CUtensorMap m1, m2, m1a;
+  int rc = encode_nhwc_map(&m1, x1, d.c, d.w, d.h, nb1, d.x1_stride_w, d.x1_stride_h, nb1 > 1 ? d.x1_stride_n : (int64_t)d.h * d.x1_stride_h,
                            tw, th, dl);
   if (rc != STM_OK) return rc;
-  rc = encode_nhwc_map(&m2, x2, d.c, d.w, d.h, d.batch, d.x2_stride_w, d.x2_stride_h, d.batch > 1 ? d.x2_stride_n : (int64_t)d.h * d.x2_stride_h,
+  rc = encode_nhwc_map(&m2, x2, d.c, d.w, d.h, nb2, d.x2_stride_w, d.x2_stride_h, nb2 > 1 ? d.x2_stride_n : (int64_t)d.h * d.x2_stride_h,
                        args.rw, args.rh, dl);
   if (rc != STM_OK) return rc;
+  m1a = m1;
+  if (indexed && d.alt_frames > 0) {
+    if (((uintptr_t)d.x1_alt & 15) || ((d.x1_alt_stride_n | d.x1_alt_stride_h | d.x1_alt_stride_w) & 7)) {
+      set_error("x1_alt must be 16-byte aligned with strides that are multiples of 8 elements");
+      return STM_ERR_INVALID_ARGUMENT;
+    }
+    rc = encode_nhwc_map(&m1a, d.x1_alt, d.c, d.w, d.h, d.alt_frames, d.x1_alt_stride_w, d.x1_alt_stride_h,
+                         d.alt_frames > 1 ? d.x1_alt_stride_n : (int64_t)d.h * d.x1_alt_stride_h, tw, th, dl);
+    if (rc != STM_OK) return rc;
+  }
   const int grid = args.n_tiles < sm_count_corr() ? args.n_tiles : sm_count_corr();
   const int post = (d.flags & STM_CORR_RELU) ? 2 : ((d.flags & STM_CORR_LEAKY_RELU) ? 1 : 0);
 #define STM_CORR_LAUNCH(OT_, TW_)                                                                     \
   do {                                                                                                \
-    if (post == 2) return launch_t<OT_, TW_, 2>(args, m1, m2, grid, L.total, stream);                 \
-    if (post == 1) return launch_t<OT_, TW_, 1>(args, m1, m2, grid, L.total, stream);                 \
-    return launch_t<OT_, TW_, 0>(args, m1, m2, grid, L.total, stream);                                \
+    if (post == 2) return launch_t<OT_, TW_, 2>(args, m1, m2, m1a, grid, L.total, stream);                 \
+    if (post == 1) return launch_t<OT_, TW_, 1>(args, m1, m2, m1a, grid, L.total, stream);                 \
+    return launch_t<OT_, TW_, 0>(args, m1, m2, m1a, grid, L.total, stream);                                \
   } while (0)
   if (tw == 20) {
     if (d.out_dtype == STM_F32) STM_CORR_LAUNCH(float, 20);

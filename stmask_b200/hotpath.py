@@ -126,6 +126,13 @@ class HotPath(torch.nn.Module):
         for m in self.fcb:
             m.conv_adaption.to(cfg.dtype)
 
+    def _comm_stream(self, device) -> "torch.cuda.Stream":
+        st = getattr(self, "_comm", None)
+        if st is None or st.device != device:
+            st = torch.cuda.Stream(device, priority=-1)
+            self._comm = st
+        return st
+
     # ---------------------------------------------------------------- synthetic activations
     def make_inputs(self, n_frames: int, device, seed: int = 0, pinned_host: bool = False) -> Dict[str, torch.Tensor]:
         """Synthetic N(0,1) activations of the shapes the reference produces for `n_frames` frames
@@ -159,9 +166,20 @@ class HotPath(torch.nn.Module):
                 group=None) -> Dict[str, torch.Tensor]:
         out: Dict[str, torch.Tensor] = {}
         halo = None
+        comm = None
         if self.cfg.temporal_fusion and plan is not None and plan.world_size > 1:
-            # post the halo exchange first so the NVLink transfer overlaps the DCN kernels
-            halo = sharding.exchange_halo(plan, rank, [inp["tf.fpn"], inp["tf.t2s"]], group)
+            # Post the halo exchange first, on a high-priority SIDE stream: the NCCL send/recv completes only when
+            # the neighbour rank has posted its side, and on the compute stream that wait would put all ranks in
+            # lock step every step.  The compute stream joins the side stream right before the correlation, so the
+            # NVLink transfer (and any rank skew up to the DCN work's duration) hides behind the DCN kernels.
+            main = torch.cuda.current_stream()
+            if inp["tf.fpn"].is_cuda:
+                comm = self._comm_stream(inp["tf.fpn"].device)
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    halo = sharding.exchange_halo(plan, rank, [inp["tf.fpn"], inp["tf.t2s"]], group)
+            else:
+                halo = sharding.exchange_halo(plan, rank, [inp["tf.fpn"], inp["tf.t2s"]], group)
         for i, m in enumerate(self.backbone_dcn):
             out[f"dcn{i}.y"] = m(inp[f"dcn{i}.x"])
         for k, m in enumerate(self.fcb):
@@ -171,20 +189,16 @@ class HotPath(torch.nn.Module):
                 out[f"fcb.y{l}.{k}"] = y
         if self.cfg.temporal_fusion:
             n = inp["tf.fpn"].shape[0]
+            if comm is not None:
+                main.wait_stream(comm)
+                for h in halo or ():
+                    if h is not None:
+                        h.record_stream(main)
             if plan is None:
                 plan = sharding.make_plan(1, n, 1, "clip")
-            slices = sharding.pair_slices(plan, rank)
-            if slices is not None and len(slices) <= 4:
-                # whole clips on this rank: (frames[a:b-1], frames[a+1:b]) are views, one launch per clip
-                fpn, t2s = inp["tf.fpn"], inp["tf.t2s"]
-                outs = [self.temporal_fusion(fpn[a:b - 1], fpn[a + 1:b], t2s[a:b - 1], t2s[a + 1:b]) for a, b in slices]
-                if outs:
-                    out["tf.concat"] = outs[0] if len(outs) == 1 else outs
-            else:
-                fpn_ref, fpn_next = sharding.temporal_pairs(plan, rank, inp["tf.fpn"], halo[0] if halo else None)
-                t2s_ref, t2s_next = sharding.temporal_pairs(plan, rank, inp["tf.t2s"], halo[1] if halo else None)
-                if fpn_next.shape[0] > 0:
-                    out["tf.concat"] = self.temporal_fusion(fpn_ref, fpn_next, t2s_ref, t2s_next)
+            tf = self._tf_pairs(inp["tf.fpn"], inp["tf.t2s"], plan, rank, halo)
+            if tf is not None:
+                out["tf.concat"] = tf
         return out
 
     # ---------------------------------------------------------------- end to end from host memory
@@ -257,11 +271,26 @@ class HotPath(torch.nn.Module):
         halo = None
         if plan.world_size > 1:
             halo = sharding.exchange_halo(plan, rank, [inp["tf.fpn"], inp["tf.t2s"]], group)
-        fpn_ref, fpn_next = sharding.temporal_pairs(plan, rank, inp["tf.fpn"], halo[0] if halo else None)
-        t2s_ref, t2s_next = sharding.temporal_pairs(plan, rank, inp["tf.t2s"], halo[1] if halo else None)
+        tf = self._tf_pairs(inp["tf.fpn"], inp["tf.t2s"], plan, rank, halo)
+        return {} if tf is None else {"tf.concat": tf}
+
+    def _tf_pairs(self, fpn, t2s, plan, rank, halo):
+        """relu(cat[correlate(fpn[t-1], fpn[t]) / C, t2s[t-1], t2s[t]]) for every (t-1, t) pair whose frame t is local:
+        ONE launch that reads the pairs straight out of the frame batch (+ the received halo frames) through index
+        arrays — no gathered copies.  bf16 runs the pair-indexed tcgen05 kernel; fp32 gathers first."""
+        if fpn.dtype == torch.bfloat16 and fpn.is_cuda:
+            ref_idx, next_idx = sharding.pair_index_tensors(plan, rank, fpn.device)
+            if next_idx.numel() == 0:
+                return None
+            from .temporal_fusion import padded_corr_channels
+            return ops.correlation_pairs(fpn, ref_idx, next_idx, CORR_PATCH, 1, scale=1.0 / fpn.shape[1], relu=True, feats=t2s,
+                                         halo=halo[0] if halo else None, feats_halo=halo[1] if halo else None,
+                                         feat_channel_offset=padded_corr_channels(CORR_PATCH))
+        fpn_ref, fpn_next = sharding.temporal_pairs(plan, rank, fpn, halo[0] if halo else None)
+        t2s_ref, t2s_next = sharding.temporal_pairs(plan, rank, t2s, halo[1] if halo else None)
         if fpn_next.shape[0] == 0:
-            return {}
-        return {"tf.concat": self.temporal_fusion(fpn_ref, fpn_next, t2s_ref, t2s_next)}
+            return None
+        return self.temporal_fusion(fpn_ref, fpn_next, t2s_ref, t2s_next)
 
     def temporal_fusion(self, fpn_ref, fpn_next, t2s_ref, t2s_next):
         from .temporal_fusion import correlate_concat

@@ -437,6 +437,92 @@ def correlation(x1: torch.Tensor, x2: torch.Tensor, patch_size: int = 11, dilati
     return out
 
 
+def correlation_pairs(x: torch.Tensor, ref_index: torch.Tensor, next_index: torch.Tensor, patch_size: int = 11,
+                      dilation_patch: int = 1, *, scale: float = 1.0, leaky_slope: Optional[float] = None, relu: bool = False,
+                      feats: Optional[torch.Tensor] = None, halo: Optional[torch.Tensor] = None,
+                      feats_halo: Optional[torch.Tensor] = None, feat_channel_offset: Optional[int] = None) -> torch.Tensor:
+    """Temporal-fusion cost volume straight out of a FRAME BATCH: pair i correlates frame ref_index[i] with frame
+    next_index[i] of `x` [F, C, H, W] (and, with `feats` [F, Ct, H, W], concatenates feats[ref_index[i]],
+    feats[next_index[i]] behind it) — no gathered copies of the (t-1, t) pairs.  A ref_index value v >= F addresses
+    frame v - F of `halo` / `feats_halo`: the one-frame halos received from the neighbour rank (sharding.py).
+    Indices are int32 device tensors.  bf16 / tcgen05 only; channels-last output [n_pairs, Cout, H, W]."""
+    _require_cuda(x, "x")
+    if x.dim() != 4:
+        raise ValueError("x must be [F, C, H, W]")
+    if ref_index.dtype != torch.int32 or next_index.dtype != torch.int32 or ref_index.shape != next_index.shape or ref_index.dim() != 1:
+        raise TypeError("ref_index / next_index must be 1-D int32 tensors of equal length")
+    if not ref_index.is_cuda or not next_index.is_cuda:
+        raise RuntimeError("ref_index / next_index must be CUDA tensors")
+    if x.dtype != torch.bfloat16:
+        raise TypeError("correlation_pairs runs on the tcgen05 backend: bf16 only")
+    P, d = int(patch_size), int(dilation_patch)
+    if P < 1 or P % 2 == 0 or d < 1:
+        raise ValueError("patch_size must be odd and positive, dilation_patch >= 1")
+    f, c, h, w = x.shape
+    n = ref_index.numel()
+    a = to_nhwc(x)
+    flags = 0
+    if leaky_slope is not None:
+        flags |= L.CORR_LEAKY_RELU
+    if relu:
+        flags |= L.CORR_RELU
+    fc = 0
+    ft = None
+    if feats is not None:
+        _require_cuda(feats, "feats")
+        if feats.dim() != 4 or feats.shape[0] != f or tuple(feats.shape[2:]) != (h, w) or feats.dtype != x.dtype:
+            raise ValueError("feats must be [F, Ct, H, W] matching x")
+        ft = to_nhwc(feats)
+        fc = ft.shape[1]
+        flags |= L.CORR_COPY_FEATS
+    ha = hf = None
+    if halo is not None and halo.shape[0] > 0:
+        if tuple(halo.shape[1:]) != (c, h, w) or halo.dtype != x.dtype:
+            raise ValueError("halo must be [Fh, C, H, W] matching x")
+        ha = to_nhwc(halo)
+        if feats is not None:
+            if feats_halo is None or feats_halo.shape[0] != halo.shape[0] or tuple(feats_halo.shape[1:]) != (fc, h, w):
+                raise ValueError("feats_halo must be [Fh, Ct, H, W]")
+            hf = to_nhwc(feats_halo.to(x.dtype))
+    foff = P * P
+    if feat_channel_offset is not None:
+        if feats is None or int(feat_channel_offset) < P * P:
+            raise ValueError("feat_channel_offset needs feats and must be >= patch_size**2")
+        foff = int(feat_channel_offset)
+    out = torch.empty((n, foff + 2 * fc if feats is not None else P * P, h, w), dtype=x.dtype, device=x.device,
+                      memory_format=torch.channels_last)
+    if out.numel() == 0:
+        return out
+    desc = L.StmCorrDesc()
+    desc.batch, desc.h, desc.w, desc.c = n, h, w, c
+    desc.patch, desc.dilation_patch = P, d
+    desc.dtype = desc.out_dtype = L.STM_BF16
+    desc.flags, desc.backend = flags, L.BACKEND_TCGEN05
+    desc.scale, desc.leaky_slope = float(scale), float(leaky_slope or 0.0)
+    desc.x1_stride_n, desc.x1_stride_h, desc.x1_stride_w = a.stride(0), a.stride(2), a.stride(3)
+    desc.x2_stride_n, desc.x2_stride_h, desc.x2_stride_w = a.stride(0), a.stride(2), a.stride(3)
+    desc.out_stride_n, desc.out_stride_c, desc.out_stride_h, desc.out_stride_w = out.stride()
+    desc.feat_c, desc.feat_dtype = fc, L.STM_BF16
+    desc.feat_c_offset = foff if feats is not None else 0
+    if ft is not None:
+        desc.feat_a_stride_n, desc.feat_a_stride_h, desc.feat_a_stride_w = ft.stride(0), ft.stride(2), ft.stride(3)
+        desc.feat_b_stride_n, desc.feat_b_stride_h, desc.feat_b_stride_w = ft.stride(0), ft.stride(2), ft.stride(3)
+    desc.x1_index, desc.x2_index = ref_index.data_ptr(), next_index.data_ptr()
+    desc.x1_frames = desc.x2_frames = f
+    if ha is not None:
+        desc.alt_frames = ha.shape[0]
+        desc.x1_alt = ha.data_ptr()
+        desc.x1_alt_stride_n, desc.x1_alt_stride_h, desc.x1_alt_stride_w = ha.stride(0), ha.stride(2), ha.stride(3)
+        if hf is not None:
+            desc.feat_a_alt = hf.data_ptr()
+            desc.feat_a_alt_stride_n, desc.feat_a_alt_stride_h, desc.feat_a_alt_stride_w = hf.stride(0), hf.stride(2), hf.stride(3)
+    with torch.cuda.device(x.device):
+        rc = L.lib().stm_correlation_fwd(C.byref(desc), a.data_ptr(), a.data_ptr(), ft.data_ptr() if ft is not None else None,
+                                         ft.data_ptr() if ft is not None else None, out.data_ptr(), _stream(x))
+    L.check(rc, "stm_correlation_fwd")
+    return out
+
+
 def correlation_backend(shape: Sequence[int], dtype: torch.dtype, patch_size: int = 11, dilation_patch: int = 1,
                         backend: str = "auto") -> str:
     b, c, h, w = shape

@@ -203,6 +203,21 @@ def pair_indices(plan: ShardPlan, rank: int) -> Tuple[List[int], List[int]]:
     return ref_idx, next_idx
 
 
+_PAIR_INDEX_CACHE: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def pair_index_tensors(plan: ShardPlan, rank: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`pair_indices` as int32 device tensors (what `ops.correlation_pairs` takes), cached per plan / rank / device so
+    a step does no host-to-device copy for them."""
+    key = (plan.world_size, plan.n_clips, plan.frames_per_clip, plan.mode, rank, str(device))
+    hit = _PAIR_INDEX_CACHE.get(key)
+    if hit is None:
+        ref_idx, next_idx = pair_indices(plan, rank)
+        hit = (torch.tensor(ref_idx, dtype=torch.int32, device=device), torch.tensor(next_idx, dtype=torch.int32, device=device))
+        _PAIR_INDEX_CACHE[key] = hit
+    return hit
+
+
 def pair_slices(plan: ShardPlan, rank: int) -> Optional[List[Tuple[int, int]]]:
     """When no pair of this rank crosses a shard boundary, the pairs of a segment are simply
     (frames[a:b-1], frames[a+1:b]): return the [a, b) ranges so the caller can use VIEWS (zero copies).

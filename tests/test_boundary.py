@@ -34,7 +34,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name)
     lib.stm_version.restype = ctypes.c_int
-    assert lib.stm_version() == 2
+    assert lib.stm_version() == 3
     lib.stm_last_error.restype = ctypes.c_char_p
     assert lib.stm_last_error() == b""
 
@@ -47,7 +47,7 @@ def test_python_binding_covers_the_header():
     # struct layouts: sizes follow from the header's field lists (no padding surprises)
     assert ctypes.sizeof(_lib.StmDcnConv) == 16 * 4
     assert ctypes.sizeof(_lib.StmDcnProblem) == 5 * 4 + 4 + 8 * (4 + 5 + 5 + 4)
-    assert ctypes.sizeof(_lib.StmCorrDesc) == 12 * 4 + 8 * 10 + 2 * 4 + 8 * 6 + 2 * 4
+    assert ctypes.sizeof(_lib.StmCorrDesc) == 12 * 4 + 8 * 10 + 2 * 4 + 8 * 6 + 2 * 4 + 2 * 8 + 4 * 4 + 2 * 8 + 6 * 8
 
 
 def test_abi_validates_arguments_without_a_gpu():

@@ -401,6 +401,35 @@ def test_error_conventions(cuda_device):
     assert ops.deform_conv2d(x[:0], torch.zeros(0, 18, 5, 5, device=cuda_device), w, padding=1).shape == (0, 8, 5, 5)
 
 
+def test_correlation_pairs_reads_frames_and_halos_in_place(cuda_device):
+    """Pair-indexed kernel (frames + received halos through index arrays) == the same kernel on gathered copies."""
+    from stmask_b200 import sharding
+    from stmask_b200.temporal_fusion import correlate_concat
+    ops = _ops()
+    torch.manual_seed(11)
+    mk = lambda n, c: torch.randn(n, c, 24, 40, device=cuda_device).bfloat16().contiguous(memory_format=torch.channels_last)
+    plan = sharding.make_plan(3, 6, 2, "frame")                 # rank 1 owns frames 3..5 of 3 clips: 3 halos, 9 pairs
+    fpn, t2s = mk(9, 256), mk(9, 256)
+    wire = torch.randn(3, 24, 40, 512, device=cuda_device).bfloat16()       # halos as they arrive: NHWC [fpn | t2s]
+    halo_fpn, halo_t2s = wire.permute(0, 3, 1, 2)[:, :256], wire.permute(0, 3, 1, 2)[:, 256:]
+    ref_idx, next_idx = sharding.pair_index_tensors(plan, 1, cuda_device)
+    assert ref_idx.numel() == 9 and int(ref_idx.max()) >= 9
+    got = ops.correlation_pairs(fpn, ref_idx, next_idx, 11, 1, scale=1 / 256, relu=True, feats=t2s, halo=halo_fpn,
+                                feats_halo=halo_t2s, feat_channel_offset=128)
+    fr, fn = sharding.temporal_pairs(plan, 1, fpn, halo_fpn)
+    tr, tn = sharding.temporal_pairs(plan, 1, t2s, halo_t2s)
+    want = correlate_concat(fr, fn, tr, tn, 11, 1, padded=True)
+    assert got.shape == want.shape == (9, 640, 24, 40)
+    assert torch.equal(got, want)
+    # no features, no halo: plain indexed cost volume
+    plan1 = sharding.make_plan(2, 4, 1, "clip")
+    r1, n1 = sharding.pair_index_tensors(plan1, 0, cuda_device)
+    x = mk(8, 128)
+    got = ops.correlation_pairs(x, r1, n1, 11, 1)
+    want = ops.correlation(x[r1.long()], x[n1.long()], 11, 1, channels_last=True)
+    assert torch.equal(got, want)
+
+
 # ------------------------------------------------------------------------------------------
 # the hot path end to end from host memory == the device-resident step, bit for bit
 # ------------------------------------------------------------------------------------------
@@ -416,8 +445,12 @@ def test_forward_streamed_equals_resident_step(cuda_device):
     want = dict(hp._frames_only({k: v for k, v in d_in.items() if not k.startswith("tf.")}))
     want.update(hp._tf_only({k: v for k, v in d_in.items() if k.startswith("tf.")}, plan, 0, None))
     whole = hp(d_in, plan, 0)                                  # the schedulable unit bench.py times
-    tf_whole = whole["tf.concat"] if not isinstance(whole["tf.concat"], list) else torch.cat(whole["tf.concat"], 0)
-    assert want["tf.concat"].shape[0] == 8 and torch.equal(want["tf.concat"], tf_whole)
+    assert want["tf.concat"].shape[0] == 8 and torch.equal(want["tf.concat"], whole["tf.concat"])
+    # ... and the pair-indexed kernel equals the reference-order concat of gathered pairs
+    from stmask_b200.temporal_fusion import correlate_concat, unpad_concat
+    fr, fn = sharding.temporal_pairs(plan, 0, d_in["tf.fpn"], None)
+    tr, tn = sharding.temporal_pairs(plan, 0, d_in["tf.t2s"], None)
+    assert torch.equal(unpad_concat(whole["tf.concat"]), correlate_concat(fr, fn, tr, tn, channels_last=True, padded=True)[:, [*range(121), *range(128, 640)]])
     host_out = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in want.items()}
     io = StreamedIO(cuda_device, chunk_frames=4)               # 4 + 4 + 2 frames
     for _ in range(2):                                         # second pass reuses the staging buffers
