@@ -264,6 +264,8 @@ def main():
     ap.add_argument("--backend", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--clips-per-gpu", type=int, default=CLIPS_PER_GPU)
     ap.add_argument("--frames-per-clip", type=int, default=FRAMES_PER_CLIP)
+    ap.add_argument("--sharding", default="auto", choices=["auto", "clip", "frame"],
+                    help="auto = frame-wise cuts (halo exchange in the timed region) for N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=12, help="frames per chunk of the streamed end-to-end path")
@@ -296,7 +298,8 @@ def main():
         raise SystemExit("stmask_b200 needs an sm_100 (B200) device; there is no fallback")
 
     n_clips = args.clips_per_gpu * world
-    plan = sharding.make_plan(n_clips, args.frames_per_clip, world, "frame" if world > 1 else "clip")
+    mode = args.sharding if args.sharding != "auto" else ("frame" if world > 1 else "clip")
+    plan = sharding.make_plan(n_clips, args.frames_per_clip, world, mode)
     n_local = plan.local_frames(rank)
     total_frames = n_clips * args.frames_per_clip
     hp = HotPath(hp_cfg, dev, seed=0)
@@ -323,14 +326,24 @@ def main():
     barrier()
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import gc
+    gc.collect()
+    gc.disable()              # a cyclic-GC pause inside the timed region would stall this rank and, through the halos, all others
     with ClockSampler(local_rank) as clocks:
         barrier()
         e0.record()
+        marks = []
         for _ in range(args.steps):
             out = step(inp)
+            if os.environ.get("STM_BENCH_TRACE"):
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
         e1.record()
         barrier()
+    gc.enable()
     ms = e0.elapsed_time(e1)
+    if marks:
+        print(f"rank {rank} per-step ms:", " ".join(f"{a.elapsed_time(b):.2f}" for a, b in zip([e0] + marks[:-1], marks)), file=sys.stderr)
     launches = _lib.launch_count() - n0
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:

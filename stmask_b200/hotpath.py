@@ -126,6 +126,13 @@ class HotPath(torch.nn.Module):
         for m in self.fcb:
             m.conv_adaption.to(cfg.dtype)
 
+    @property
+    def _halo_buffers(self) -> dict:
+        b = getattr(self, "_halo_bufs", None)
+        if b is None:
+            b = self._halo_bufs = {}
+        return b
+
     def _comm_stream(self, device) -> "torch.cuda.Stream":
         st = getattr(self, "_comm", None)
         if st is None or st.device != device:
@@ -177,7 +184,9 @@ class HotPath(torch.nn.Module):
                 comm = self._comm_stream(inp["tf.fpn"].device)
                 comm.wait_stream(main)
                 with torch.cuda.stream(comm):
-                    halo = sharding.exchange_halo(plan, rank, [inp["tf.fpn"], inp["tf.t2s"]], group)
+                    # persistent message / receive buffers: the side stream waited for the previous step's
+                    # correlation (comm.wait_stream above), so reusing them is safe and nothing is allocated here
+                    halo = sharding.exchange_halo(plan, rank, [inp["tf.fpn"], inp["tf.t2s"]], group, self._halo_buffers)
             else:
                 halo = sharding.exchange_halo(plan, rank, [inp["tf.fpn"], inp["tf.t2s"]], group)
         for i, m in enumerate(self.backbone_dcn):
@@ -191,9 +200,6 @@ class HotPath(torch.nn.Module):
             n = inp["tf.fpn"].shape[0]
             if comm is not None:
                 main.wait_stream(comm)
-                for h in halo or ():
-                    if h is not None:
-                        h.record_stream(main)
             if plan is None:
                 plan = sharding.make_plan(1, n, 1, "clip")
             tf = self._tf_pairs(inp["tf.fpn"], inp["tf.t2s"], plan, rank, halo)

@@ -96,9 +96,17 @@ def make_plan(n_clips: int, frames_per_clip: int, world_size: int, mode: str = "
                 add(r, clip, a, b)
                 f += b - a
     else:
+        # frames_per_clip = base * world_size + extra: `extra` ranks take base + 1 frames of a clip.  Which ranks do
+        # rotates from clip to clip, so the per-rank totals stay balanced (36 frames over 8 ranks: 4/5 alternate and
+        # every rank ends up with 9 frames per two clips instead of 8 vs 10).
+        base, extra = divmod(frames_per_clip, world_size)
         for clip in range(n_clips):
+            first = (clip * extra) % world_size
+            a = 0
             for r in range(world_size):
-                add(r, clip, r * frames_per_clip // world_size, (r + 1) * frames_per_clip // world_size)
+                b = a + base + (1 if (r - first) % world_size < extra else 0)
+                add(r, clip, a, b)
+                a = b
     halos = []
     for r in range(world_size):
         for s in segs[r]:
@@ -109,64 +117,87 @@ def make_plan(n_clips: int, frames_per_clip: int, world_size: int, mode: str = "
     return ShardPlan(world_size, n_clips, frames_per_clip, mode, segs, halos)
 
 
-def exchange_halo(plan: ShardPlan, rank: int, feats: Sequence[torch.Tensor], group=None) -> List[Optional[torch.Tensor]]:
-    """Send the last-frame features of every local segment that another rank continues, receive the
-    halos this rank needs.  `feats` = per-frame feature tensors of the local batch, each
-    [n_local, C, H, W] (e.g. fpn_feat and T2S_feat); they are packed into ONE message per
-    neighbour, NHWC on the wire: [n_boundaries, H, W, sum(C)].
+_SEND_ROWS_CACHE: Dict[Tuple, torch.Tensor] = {}
 
-    Returns, for each f in feats, a tensor [n_recv, C, H, W] ordered like plan.recv_halos(rank)
-    (None when this rank receives nothing).  All isend/irecv of the step go out in one batch."""
+
+def _send_rows(plan: ShardPlan, rank: int, dst: int, rows: List[int], device) -> torch.Tensor:
+    key = (plan.world_size, plan.n_clips, plan.frames_per_clip, plan.mode, rank, dst, str(device))
+    t = _SEND_ROWS_CACHE.get(key)
+    if t is None:
+        t = torch.tensor(rows, dtype=torch.long, device=device)
+        _SEND_ROWS_CACHE[key] = t
+    return t
+
+
+def exchange_halo(plan: ShardPlan, rank: int, feats: Sequence[torch.Tensor], group=None,
+                  buffers: Optional[dict] = None) -> List[Optional[torch.Tensor]]:
+    """Send the last-frame features of every local segment that another rank continues, receive the
+    halos this rank needs.  `buffers` (a dict the caller keeps between steps) makes the message and receive
+    buffers persistent: no allocation inside a step (a cudaMalloc in the caching allocator is a multi-ms,
+    device-synchronising stall that the halo dependency then propagates to every rank).  `feats` = per-frame feature tensors of the local batch, each
+    [n_local, C, H, W] (e.g. fpn_feat and T2S_feat).
+
+    Per neighbour and feature tensor ONE message: the boundary frames gathered by one index_select on the NHWC
+    view (`[n_boundaries, H, W, C]`, the kernels' layout, whatever the local memory format is), received
+    straight into the buffer the correlation kernel reads.  All isend/irecv of a step go out in one batch
+    (few large messages: many small ones cost NCCL far more than the gather).
+
+    Returns, for each f in feats, a channels-last tensor [n_recv, C, H, W] ordered like plan.recv_halos(rank)
+    (None when this rank receives nothing)."""
     sends = plan.send_halos(rank)
     recvs = plan.recv_halos(rank)
     if plan.world_size == 1 or (not sends and not recvs):
         return [None for _ in feats]
-    ref = feats[0]
-    chans = [f.shape[1] for f in feats]
-    hw = tuple(ref.shape[2:])
-    # wire format: [n_boundaries, H, W, sum(C)] contiguous == the kernels' NHWC layout, whatever the
-    # local memory format is (P2P ops need contiguous buffers; both sides must agree)
     seg_of = {(s.clip, s.stop): s for s in plan.segments[rank]}
     ops_, keep = [], []
     by_dst: Dict[int, List[Halo]] = {}
     for h in sends:
         by_dst.setdefault(h.dst, []).append(h)
     for dst, hs in sorted(by_dst.items()):
-        idx = [seg_of[(h.clip, h.frame)].offset + seg_of[(h.clip, h.frame)].length - 1 for h in hs]
-        idx_t = torch.as_tensor(idx, device=ref.device)
-        msg = torch.cat([f.index_select(0, idx_t).permute(0, 2, 3, 1) for f in feats], dim=3).contiguous()
-        keep.append(msg)
-        ops_.append(dist.P2POp(dist.isend, msg, dst, group))
+        rows = [seg_of[(h.clip, h.frame)].offset + seg_of[(h.clip, h.frame)].length - 1 for h in hs]
+        idx_t = _send_rows(plan, rank, dst, rows, feats[0].device)
+        for j, f in enumerate(feats):
+            nhwc = f.permute(0, 2, 3, 1)
+            if buffers is not None:
+                msg = buffers.get(("send", dst, j))
+                if msg is None or msg.shape != (len(rows),) + tuple(nhwc.shape[1:]) or msg.dtype != f.dtype or msg.device != f.device:
+                    msg = buffers[("send", dst, j)] = f.new_empty((len(rows),) + tuple(nhwc.shape[1:]))
+                torch.index_select(nhwc, 0, idx_t, out=msg)
+            else:
+                msg = nhwc.index_select(0, idx_t)                     # contiguous [n, H, W, C]
+            keep.append(msg)
+            ops_.append(dist.P2POp(dist.isend, msg, dst, group))
     by_src: Dict[int, List[Halo]] = {}
     for h in recvs:
         by_src.setdefault(h.src, []).append(h)
-    bufs: Dict[int, torch.Tensor] = {}
+    bufs: Dict[int, List[torch.Tensor]] = {}
     for src, hs in sorted(by_src.items()):
-        buf = torch.empty((len(hs),) + hw + (sum(chans),), dtype=ref.dtype, device=ref.device)
-        bufs[src] = buf
-        ops_.append(dist.P2POp(dist.irecv, buf, src, group))
+        bufs[src] = []
+        for j, f in enumerate(feats):
+            shape = (len(hs),) + tuple(f.shape[2:]) + (f.shape[1],)
+            b = buffers.get(("recv", src, j)) if buffers is not None else None
+            if b is None or b.shape != shape or b.dtype != f.dtype or b.device != f.device:
+                b = f.new_empty(shape)
+                if buffers is not None:
+                    buffers[("recv", src, j)] = b
+            bufs[src].append(b)
+        for b in bufs[src]:
+            ops_.append(dist.P2POp(dist.irecv, b, src, group))
     for w in dist.batch_isend_irecv(ops_):
         w.wait()
     if not recvs:
         return [None for _ in feats]
-    # reorder to plan.recv_halos(rank) order
-    pos = {}
-    for src, hs in by_src.items():
-        for i, h in enumerate(hs):
-            pos[(h.clip, h.frame)] = (src, i)
-    rows = [bufs[pos[(h.clip, h.frame)][0]][pos[(h.clip, h.frame)][1]] for h in recvs]
-    stacked = rows[0].new_empty((len(rows),) + tuple(rows[0].shape)) if len(by_src) > 1 else None
-    if stacked is None:
-        src0 = next(iter(by_src))
-        order = [pos[(h.clip, h.frame)][1] for h in recvs]
-        stacked = bufs[src0] if order == list(range(len(order))) else bufs[src0][order]
-    else:
-        torch.stack(rows, 0, out=stacked)
-    nchw = stacked.permute(0, 3, 1, 2)          # NCHW-shaped view of NHWC memory (channels-last)
-    out, c0 = [], 0
-    for c in chans:
-        out.append(nchw[:, c0:c0 + c])
-        c0 += c
+    out = []
+    for j in range(len(feats)):
+        if len(by_src) == 1:
+            nhwc = bufs[next(iter(by_src))][j]                         # already in plan.recv_halos order
+        else:
+            pos = {}
+            for src, hs in by_src.items():
+                for i, h in enumerate(hs):
+                    pos[(h.clip, h.frame)] = (src, i)
+            nhwc = torch.stack([bufs[pos[(h.clip, h.frame)][0]][j][pos[(h.clip, h.frame)][1]] for h in recvs], 0)
+        out.append(nhwc.permute(0, 3, 1, 2))                          # NCHW-shaped view of NHWC memory (channels-last)
     return out
 
 
