@@ -1,5 +1,5 @@
 """Run ONE hot-path operator a few times (for ncu captures and quick timing).
-    python tools/profile_case.py fcb35|fcb33|fcb53|bb128s2|bb128|bb256|bb512s2|corr|corrsweep [--frames 72] [--reps 5] [--backend auto]
+    python tools/profile_case.py fcb35|fcb33|fcb53|bb128s2|bb128|bb256|bb512s2|corr|corrpairs|corrsweep [--frames 72] [--reps 5] [--backend auto]
 """
 import argparse
 import os
@@ -83,6 +83,15 @@ elif a.case == "corr":
     foff = None if os.environ.get("STM_CORR_UNPADDED") else 128
     fn = lambda: ops.correlation(x1, x2, 11, 1, scale=1 / 256, relu=True, feats=(t1, t2), channels_last=True, backend=a.backend,
                                  feat_channel_offset=foff)
+    print("algorithmic (SURVEY 8d) GB/s = reported x", (633 + 512) / (633 + 1024.0))
+    timeit(fn, nbytes=n * 960 * (633 + 2 * 256 + 2 * 256) * 2.0)
+elif a.case == "corrpairs":      # the hot path's temporal fusion: (t-1, t) pairs read in place from one F-frame clip
+    from stmask_b200 import sharding
+    x = torch.randn(F, 256, 24, 40, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    t = torch.randn_like(x)
+    ri, ni = sharding.pair_index_tensors(sharding.make_plan(1, F, 1), 0, x.device)
+    fn = lambda: ops.correlation_pairs(x, ri, ni, 11, 1, scale=1 / 256, relu=True, feats=t, feat_channel_offset=128)
+    n = F - 1
     print("algorithmic (SURVEY 8d) GB/s = reported x", (633 + 512) / (633 + 1024.0))
     timeit(fn, nbytes=n * 960 * (633 + 2 * 256 + 2 * 256) * 2.0)
 elif a.case == "corrsweep":       # BASELINE.json configs[1]: batch 8 over P3..P7, plain cost volume
