@@ -59,7 +59,11 @@ def _worker(rank, world, port, mode, n_clips, fpc, q):
         if rank == 1:   # exercise the channels-last message path on one rank's send side too
             loc1 = loc1.contiguous(memory_format=torch.channels_last)
             loc2 = loc2.contiguous(memory_format=torch.channels_last)
-        h1, h2 = exchange_halo(plan, rank, [loc1, loc2])
+        bufs = {}                                  # persistent message / receive buffers: second step must reuse them
+        exchange_halo(plan, rank, [torch.zeros_like(loc1), torch.zeros_like(loc2)], buffers=bufs)
+        ptrs = sorted((k, v.data_ptr()) for k, v in bufs.items())
+        h1, h2 = exchange_halo(plan, rank, [loc1, loc2], buffers=bufs)
+        assert ptrs == sorted((k, v.data_ptr()) for k, v in bufs.items())
         ref1, nxt1 = temporal_pairs(plan, rank, loc1, h1)
         ref2, nxt2 = temporal_pairs(plan, rank, loc2, h2)
         # expected pairs straight from the global tensors
@@ -76,7 +80,19 @@ def _worker(rank, world, port, mode, n_clips, fpc, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,n_clips,fpc", [("frame", 3, 8), ("clip", 3, 5), ("clip", 4, 4)])
+def test_frame_mode_rotates_the_odd_frames_so_ranks_stay_balanced():
+    plan = make_plan(16, 36, 8, "frame")       # 36 frames over 8 ranks: 4 or 5 per clip
+    assert [plan.local_frames(r) for r in range(8)] == [72] * 8
+    assert len(plan.halos) == 16 * 7
+    for clip in range(16):                      # every clip is covered exactly once, in order
+        segs = sorted((s.start, s.stop) for r in range(8) for s in plan.segments[r] if s.clip == clip)
+        assert segs[0][0] == 0 and segs[-1][1] == 36 and all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+    plan = make_plan(3, 5, 4, "frame")          # fewer frames than ranks * 2: some ranks skip a clip's remainder
+    assert sum(plan.local_frames(r) for r in range(4)) == 15
+    assert sum(plan.local_pairs(r) for r in range(4)) == 3 * 4
+
+
+@pytest.mark.parametrize("mode,n_clips,fpc", [("frame", 3, 8), ("frame", 3, 7), ("clip", 3, 5), ("clip", 4, 4)])
 def test_halo_exchange_world_size_2_gloo(mode, n_clips, fpc):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
