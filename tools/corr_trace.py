@@ -6,10 +6,12 @@ sys.path.insert(0, ROOT)
 import torch
 from stmask_b200 import ops
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 71
-x1 = torch.randn(n, 256, 24, 40, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
-x2, t1, t2 = torch.randn_like(x1), torch.randn_like(x1), torch.randn_like(x1)
+from stmask_b200 import sharding
+x = torch.randn(n + 1, 256, 24, 40, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+t = torch.randn_like(x)
+ri, ni = sharding.pair_index_tensors(sharding.make_plan(1, n + 1, 1), 0, x.device)
 buf = torch.zeros(148 * 64, dtype=torch.int64, device="cuda")
-run = lambda: ops.correlation(x1, x2, 11, 1, scale=1 / 256, relu=True, feats=(t1, t2), channels_last=True, feat_channel_offset=128)
+run = lambda: ops.correlation_pairs(x, ri, ni, 11, 1, scale=1 / 256, relu=True, feats=t, feat_channel_offset=128)
 run(); torch.cuda.synchronize()
 os.environ["STM_DEBUG_BUF"] = hex(buf.data_ptr())
 run(); torch.cuda.synchronize()
