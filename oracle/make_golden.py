@@ -11,6 +11,9 @@ Sources of truth:
                         FCB(ada) and FCB(ali), imported from /root/reference over the torchvision stand-in
   correlate.npz         the reference's own correlate() (track_to_segment_head.py:40-62) over the
                         shifted-product stand-in, P=11, d=1/2
+  detections.npz        FCB(ada) 3x5 head -> class confidences -> the reference's OWN candidate filter and
+                        cross-class fast NMS (TF_utils.py:68-74, detection_TF.py:56-134): the inputs, the
+                        reference's logits and the detections it keeps ("identical detections after fast NMS")
   backbone_dcn.npz      the reference's ResNetBackbone DCN placement (backbone.py:105-138) for the R50/R101
                         configs, and a Bottleneck DCN-branch forward (backbone.py:20-26,45)
 """
@@ -178,6 +181,46 @@ def _backbone_dcn():
     np.savez_compressed(os.path.join(OUT, "backbone_dcn.npz"), **out)
 
 
+def _detections():
+    """One FPN level (24x40, one prior per pixel) through the reference's FeatureAlign head and Detect_TF."""
+    fa_mod = rh.load_featurealign()
+    det_mod = rh.load_detect()
+    torch.manual_seed(4242)
+    C, H, W, ks = 64, 24, 40, (3, 5)
+    m = fa_mod.FeatureAlign(C, 41, kernel_size=ks, deformable_groups=1, use_pred_offset=True)
+    torch.nn.init.normal_(m.conv_offset.weight, std=0.5)
+    torch.nn.init.normal_(m.conv_adaption.weight, std=(C * 15) ** -0.5)
+    torch.nn.init.normal_(m.conv.weight, std=4.0 * (C * 15) ** -0.5)       # confident logits, so NMS has work to do
+    torch.nn.init.normal_(m.conv.bias, std=0.5)
+    x, shape = torch.randn(1, C, H, W), torch.randn(1, 4, H, W)
+    with torch.no_grad():
+        logits = m(x.clone(), shape)                                           # [1, 41, H, W]
+    conf = torch.softmax(logits[0].permute(1, 2, 0).reshape(H * W, 41), -1)    # one prior per pixel (STMask.py eval)
+    # boxes: centred on the prior's pixel, random size, xyxy normalised; neighbours overlap heavily
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    cx, cy = ((xs + 0.5) / W).reshape(-1), ((ys + 0.5) / H).reshape(-1)
+    bw, bh = 0.04 + 0.12 * torch.rand(H * W), 0.06 + 0.2 * torch.rand(H * W)
+    boxes = torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
+    centerness = 0.3 + 0.7 * torch.rand(H * W)
+    # the reference's candidate filter (TF_utils.py:68-74, cfg.eval_conf_thresh = 0.05) ...
+    conf_t = conf.t().contiguous()
+    keep = torch.max(conf_t[1:, :], dim=0)[0] > 0.05
+    cand = {"conf": conf_t[:, keep].t(), "box": boxes[keep], "centerness": centerness[keep],
+            "mask_coeff": torch.zeros(int(keep.sum()), 8), "track": None, "proto": None}
+    # ... and its cross-class fast NMS (detection_TF.py:56-134, nms_thresh 0.5, top_k 200)
+    det = det_mod.Detect_TF(41, 0, 200, 0.05, 0.5).detect(cand)
+    kept_prior = torch.nonzero(keep).view(-1)
+    # identify the kept detections by their prior index (boxes are unique per prior)
+    idx = [int(kept_prior[(cand["box"] == b).all(1).nonzero()[0, 0]]) for b in det["box"]]
+    assert 10 <= len(idx) <= 200, len(idx)
+    np.savez_compressed(os.path.join(OUT, "detections.npz"), x=x.numpy(), shape=shape.numpy(),
+                        w_offset=m.conv_offset.weight.detach().numpy(), w_adaption=m.conv_adaption.weight.detach().numpy(),
+                        w_conv=m.conv.weight.detach().numpy(), b_conv=m.conv.bias.detach().numpy(),
+                        boxes=boxes.numpy(), centerness=centerness.numpy(), logits=logits.numpy(),
+                        det_prior=np.asarray(idx, np.int64), det_class=det["class"].numpy().astype(np.int64),
+                        det_score=det["score"].numpy())
+
+
 def main():
     if not rh.available():
         raise SystemExit("/root/reference is not present: fixtures can only be regenerated in the build container")
@@ -188,6 +231,7 @@ def main():
     _feature_align()
     _correlate()
     _backbone_dcn()
+    _detections()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -172,3 +172,28 @@ def load_track_to_segment_head():
                                                            sanitize_coordinates_hw=sanitize_coordinates_hw),
     }
     return _load("layers/modules/track_to_segment_head.py", "_stm_ref_t2s", stubs)
+
+
+def load_detect(nms_as_miou: bool = False):
+    """reference layers/functions/detection_TF.py (Detect_TF.detect / cc_fast_nms) with its own
+    layers/box_utils.py (jaccard); masks are not involved (cfg.nms_as_miou = False as in the STMask configs)."""
+    from contextlib import contextmanager as _cm
+
+    @_cm
+    def _env(name):
+        yield
+
+    cfg = types.SimpleNamespace(nms_as_miou=nms_as_miou)
+    timer = _mod("utils.timer", env=_env)
+    utils = _mod("utils", timer=timer)
+    datasets = _mod("datasets", cfg=cfg)
+    base = {"utils": utils, "utils.timer": timer, "datasets": datasets, "mmcv": _mod("mmcv")}
+    box_utils = _load("layers/box_utils.py", "layers.box_utils", base)
+    layers = _mod("layers", box_utils=box_utils)
+    layers.__path__ = []
+    functions = _mod("layers.functions")
+    functions.__path__ = []
+    mask_utils = _mod("layers.mask_utils", generate_mask=None)
+    stubs = dict(base)
+    stubs.update({"layers": layers, "layers.box_utils": box_utils, "layers.mask_utils": mask_utils, "layers.functions": functions})
+    return _load("layers/functions/detection_TF.py", "layers.functions.detection_TF", stubs)
