@@ -11,6 +11,8 @@
  *                           <- mmcv.ops.ModulatedDeformConv2d  (named by the north star; same math as dcn_v2)
  *   stm_fcb_ali_offsets     <- the closed-form box->offset map (layers/modules/Featurealign.py:46-69)
  *   stm_fcb_ada_offsets     <- the 1x1 conv_offset on box deltas    (layers/modules/Featurealign.py:20-25,44)
+ *   stm_roi_align_fwd       <- mmcv.ops.roi_align as bbox_feat_extractor calls it
+ *                              (layers/modules/track_to_segment_head.py:65-88)
  *   stm_correlation_fwd     <- spatial_correlation_sampler.spatial_correlation_sample
  *                              + the /C, leaky-ReLU, concat, ReLU that follow it
  *                              (layers/modules/track_to_segment_head.py:53-62,
@@ -43,7 +45,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define STM_ABI_VERSION 3
+#define STM_ABI_VERSION 4
 
 typedef enum StmStatus {
   STM_OK = 0,
@@ -204,6 +206,26 @@ int stm_correlation_fwd(const StmCorrDesc* desc, const void* x1, const void* x2,
                         const void* feat_a, const void* feat_b, void* out, void* stream);
 
 int stm_correlation_backend(const StmCorrDesc* desc);
+
+/* ------------------------------------------------------------------------- */
+/* RoIAlign (average pooling) on an NHWC feature map                          */
+/* ------------------------------------------------------------------------- */
+typedef struct StmRoiAlignDesc {
+  int32_t batch, h, w, c;          /* feat: [batch, h, w, c] NHWC (channel stride 1)       */
+  int32_t n_rois;
+  int32_t pooled_h, pooled_w;      /* 7 x 7 in the reference                              */
+  int32_t sampling_ratio;          /* <= 0: adaptive grid ceil(roi_size / pooled_size)    */
+  int32_t aligned;                 /* 1: shift the box by -0.5 pixel (mmcv aligned=True)  */
+  int32_t dtype, out_dtype;        /* StmDType of feat / out                              */
+  float spatial_scale;
+  int64_t feat_stride_n, feat_stride_h, feat_stride_w;
+  int64_t out_stride_n, out_stride_c, out_stride_h, out_stride_w;   /* out: logical [n_rois, c, pooled_h, pooled_w] */
+} StmRoiAlignDesc;
+
+/* rois: float32 DEVICE array [n_rois][5] = (batch index, x1, y1, x2, y2), contiguous.
+ * out[r, c, i, j] = mean over the sample grid of bin (i, j) of the bilinearly interpolated feature;
+ * sample points outside [-1, h] x [-1, w] contribute 0, others are clamped into the map. */
+int stm_roi_align_fwd(const StmRoiAlignDesc* desc, const void* feat, const float* rois, void* out, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Layout helpers (NCHW <-> NHWC with dtype conversion), used at the module   */

@@ -21,4 +21,5 @@ from .oracle import (  # noqa: F401
     np_deform_conv2d,
     num_threads,
     out_size,
+    roi_align,
 )

@@ -14,6 +14,9 @@ Sources of truth:
   detections.npz        FCB(ada) 3x5 head -> class confidences -> the reference's OWN candidate filter and
                         cross-class fast NMS (TF_utils.py:68-74, detection_TF.py:56-134): the inputs, the
                         reference's logits and the detections it keeps ("identical detections after fast NMS")
+  roi_align.npz         torchvision.ops.roi_align (CPU) cases (aligned / legacy, adaptive / fixed sampling grid,
+                        boxes over the border) and the reference's own bbox_feat_extractor call site
+                        (track_to_segment_head.py:65-88) with its own sanitize_coordinates_hw
   backbone_dcn.npz      the reference's ResNetBackbone DCN placement (backbone.py:105-138) for the R50/R101
                         configs, and a Bottleneck DCN-branch forward (backbone.py:20-26,45)
 """
@@ -221,6 +224,32 @@ def _detections():
                         det_score=det["score"].numpy())
 
 
+def _roi_align():
+    from torchvision.ops import roi_align as tv_roi_align
+    out = {}
+    g = torch.Generator().manual_seed(77)
+    feat = torch.randn(2, 24, 12, 20, generator=g)
+    rois = torch.tensor([[0, 1.5, 2.0, 9.3, 7.7], [1, -3.0, -2.0, 5.0, 4.0], [0, 10.0, 5.0, 25.0, 14.0], [1, 3.2, 3.1, 3.9, 3.6],
+                         [0, 0.0, 0.0, 20.0, 12.0], [1, 18.5, 10.2, 19.9, 11.9], [0, 7.0, 3.0, 7.0, 3.0], [1, 30.0, 30.0, 40.0, 40.0]])
+    out["tv.feat"], out["tv.rois"] = feat.numpy(), rois.numpy()
+    cases = [("a7", (7, 7), 1.0, 0, True), ("a7_sr2", (7, 7), 1.0, 2, True), ("l7", (7, 7), 1.0, 0, False),
+             ("a3x5_s05", (3, 5), 0.5, 0, True)]
+    for name, osz, scale, sr, al in cases:
+        out[f"tv.{name}.y"] = tv_roi_align(feat, rois, osz, scale, sr, al).numpy()
+        out[f"tv.{name}.cfg"] = np.asarray([osz[0], osz[1], scale, sr, int(al)], np.float32)
+    # the reference's call site: normalised boxes -> sanitize_coordinates_hw -> roi_align(feat, [0, x1, y1, x2, y2], 7)
+    t2s = rh.load_track_to_segment_head()
+    fmap = torch.randn(1, 48, 24, 40, generator=g)
+    boxes = torch.rand(9, 4, generator=g)
+    boxes[:, 2:] = (boxes[:, :2] + 0.05 + 0.4 * torch.rand(9, 2, generator=g))          # some cross the right / bottom border
+    boxes[0] = torch.tensor([0.6, 0.7, 0.2, 0.1])                                          # swapped corners (sanitised)
+    with torch.no_grad():
+        pooled = t2s.bbox_feat_extractor(fmap, boxes.clone(), 24, 40, 7)
+    out["ref.feat"], out["ref.boxes_norm"], out["ref.y"] = fmap.numpy(), boxes.numpy(), pooled.numpy()
+    out["ref.boxes"] = rh.load_box_utils().sanitize_coordinates_hw(boxes.clone(), 24, 40).numpy()
+    np.savez_compressed(os.path.join(OUT, "roi_align.npz"), **out)
+
+
 def main():
     if not rh.available():
         raise SystemExit("/root/reference is not present: fixtures can only be regenerated in the build container")
@@ -232,6 +261,7 @@ def main():
     _correlate()
     _backbone_dcn()
     _detections()
+    _roi_align()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

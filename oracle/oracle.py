@@ -47,6 +47,8 @@ def _lib() -> ctypes.CDLL:
         lib.stm_oracle_correlate_post.argtypes = [f32p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float]
         lib.stm_oracle_fcb_ali_offsets.restype = None
         lib.stm_oracle_fcb_ali_offsets.argtypes = [f32p, f32p] + [ctypes.c_int] * 5
+        lib.stm_oracle_roi_align.restype = ctypes.c_int
+        lib.stm_oracle_roi_align.argtypes = [f32p] * 3 + [ctypes.c_int] * 7 + [ctypes.c_float, ctypes.c_int, ctypes.c_int]
         lib.stm_oracle_num_threads.restype = ctypes.c_int
         lib.stm_oracle_out_size.restype = ctypes.c_int
         lib.stm_oracle_out_size.argtypes = [ctypes.c_int] * 5
@@ -131,6 +133,21 @@ def correlate(x1, x2, patch_size: int = 11, dilation_patch: int = 1, accum64: bo
     B, P, _, H, W = out.shape
     out = out.reshape(B, P * P, H, W)
     _lib().stm_oracle_correlate_post(_ptr(out), out.size, int(np.asarray(x1).shape[1]), 0.1)
+    return out
+
+
+def roi_align(feat, rois, output_size: IntPair = 7, spatial_scale: float = 1.0, sampling_ratio: int = 0,
+              aligned: bool = True) -> np.ndarray:
+    """mmcv.ops.roi_align (avg) as the reference calls it (track_to_segment_head.py:85-86): feat [B, C, H, W],
+    rois [n, 5] = (batch index, x1, y1, x2, y2) -> [n, C, ph, pw]."""
+    feat, rois = _f32(feat), _f32(rois)
+    ph, pw = _pair(output_size)
+    B, C, H, W = feat.shape
+    out = np.empty((rois.shape[0], C, ph, pw), np.float32)
+    rc = _lib().stm_oracle_roi_align(_ptr(feat), _ptr(rois), _ptr(out), B, C, H, W, rois.shape[0], ph, pw,
+                                     float(spatial_scale), int(sampling_ratio), int(bool(aligned)))
+    if rc != 0:
+        raise ValueError("stm_oracle_roi_align: bad arguments")
     return out
 
 

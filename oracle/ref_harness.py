@@ -161,7 +161,8 @@ def load_track_to_segment_head():
     cfg = types.SimpleNamespace(use_sipmask=False, sipmask_head=4)
 
     def sanitize_coordinates_hw(box, h, w):
-        raise NotImplementedError("bbox_feat_extractor is a 'next' row (SURVEY.md §8f); only correlate is used")
+        # the reference's own layers/box_utils.py (the real module; box_utils needs only mmcv / utils / datasets stubs)
+        return load_box_utils().sanitize_coordinates_hw(box, h, w)
 
     stubs = {
         "mmcv": mmcv, "mmcv.ops": ops,
@@ -172,6 +173,26 @@ def load_track_to_segment_head():
                                                            sanitize_coordinates_hw=sanitize_coordinates_hw),
     }
     return _load("layers/modules/track_to_segment_head.py", "_stm_ref_t2s", stubs)
+
+
+_BOX_UTILS = None
+
+
+def load_box_utils():
+    """reference layers/box_utils.py (jaccard, sanitize_coordinates_hw, ...)."""
+    global _BOX_UTILS
+    if _BOX_UTILS is None:
+        from contextlib import contextmanager as _cm
+
+        @_cm
+        def _env(name):
+            yield
+
+        timer = _mod("utils.timer", env=_env)
+        base = {"utils": _mod("utils", timer=timer), "utils.timer": timer,
+                "datasets": _mod("datasets", cfg=types.SimpleNamespace(nms_as_miou=False)), "mmcv": _mod("mmcv")}
+        _BOX_UTILS = _load("layers/box_utils.py", "_stm_ref_box_utils", base)
+    return _BOX_UTILS
 
 
 def load_detect(nms_as_miou: bool = False):

@@ -234,6 +234,57 @@ void stm_oracle_fcb_ali_offsets(const float* shape, float* offset, int B, int H,
   }
 }
 
+/*
+ * RoIAlign forward, average pooling (mmcv.ops.roi_align as the reference calls it at
+ * layers/modules/track_to_segment_head.py:85-86: output_size = 7, spatial_scale = 1, sampling_ratio = 0,
+ * aligned = True).  mmcv-full 1.1.2 is not available; the arithmetic follows the published Detectron2 /
+ * torchvision RoIAlign (roi_align_forward_cpu): sample points at bin sub-cell centres, bilinear
+ * interpolation with the RoIAlign edge rule (a point outside [-1, H] x [-1, W] contributes 0, otherwise the
+ * coordinate is clamped to [0, size-1]), mean over the adaptive grid ceil(roi_size / pooled_size).
+ *   feat [B, C, H, W]   rois [n, 5] = (batch index, x1, y1, x2, y2)   out [n, C, ph, pw]
+ */
+int stm_oracle_roi_align(const float* feat, const float* rois, float* out, int B, int C, int H, int W, int n,
+                         int ph, int pw, float spatial_scale, int sampling_ratio, int aligned) {
+  if (!feat || !rois || !out || ph < 1 || pw < 1) return -1;
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < n; ++r) {
+    const float* roi = rois + (size_t)r * 5;
+    const int b = (int)roi[0];
+    const double off = aligned ? 0.5 : 0.0;
+    const double x1 = (double)roi[1] * spatial_scale - off, y1 = (double)roi[2] * spatial_scale - off;
+    const double x2 = (double)roi[3] * spatial_scale - off, y2 = (double)roi[4] * spatial_scale - off;
+    double rw = x2 - x1, rh = y2 - y1;
+    if (!aligned) { rw = rw > 1.0 ? rw : 1.0; rh = rh > 1.0 ? rh : 1.0; }
+    const double bh = rh / ph, bw = rw / pw;
+    const int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceil(rh / ph);
+    const int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceil(rw / pw);
+    const double count = (double)(gh * gw > 1 ? gh * gw : 1);
+    for (int c = 0; c < C; ++c) {
+      const float* plane = (b >= 0 && b < B) ? feat + ((size_t)b * C + c) * H * W : NULL;
+      for (int i = 0; i < ph; ++i)
+        for (int j = 0; j < pw; ++j) {
+          double acc = 0.0;
+          for (int iy = 0; iy < gh && plane; ++iy) {
+            const double yy = y1 + i * bh + (iy + 0.5) * bh / gh;
+            for (int ix = 0; ix < gw; ++ix) {
+              const double xx = x1 + j * bw + (ix + 0.5) * bw / gw;
+              if (yy < -1.0 || yy > (double)H || xx < -1.0 || xx > (double)W) continue;
+              double y = yy <= 0 ? 0 : yy, x = xx <= 0 ? 0 : xx;
+              int yl = (int)y, xl = (int)x, yh, xh;
+              if (yl >= H - 1) { yh = yl = H - 1; y = (double)yl; } else yh = yl + 1;
+              if (xl >= W - 1) { xh = xl = W - 1; x = (double)xl; } else xh = xl + 1;
+              const double ly = y - yl, lx = x - xl, hy = 1.0 - ly, hx = 1.0 - lx;
+              acc += hy * hx * plane[(size_t)yl * W + xl] + hy * lx * plane[(size_t)yl * W + xh] +
+                     ly * hx * plane[(size_t)yh * W + xl] + ly * lx * plane[(size_t)yh * W + xh];
+            }
+          }
+          out[(((size_t)r * C + c) * ph + i) * pw + j] = (float)(acc / count);
+        }
+    }
+  }
+  return 0;
+}
+
 int stm_oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -19,7 +19,7 @@ BACKEND_NAMES = {BACKEND_AUTO: "auto", BACKEND_SIMT: "simt", BACKEND_TCGEN05: "t
 DCN_RELU, DCN_MASK_SIGMOID, DCN_ZERO_OFFSET = 1, 2, 4
 CORR_LEAKY_RELU, CORR_RELU, CORR_COPY_FEATS = 1, 2, 4
 DCN_MAX_PROBLEMS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class StmError(RuntimeError):
@@ -64,6 +64,16 @@ class StmCorrDesc(C.Structure):
     ]
 
 
+class StmRoiAlignDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("n_rois", C.c_int32),
+        ("pooled_h", C.c_int32), ("pooled_w", C.c_int32), ("sampling_ratio", C.c_int32), ("aligned", C.c_int32),
+        ("dtype", C.c_int32), ("out_dtype", C.c_int32), ("spatial_scale", C.c_float),
+        ("feat_stride_n", C.c_int64), ("feat_stride_h", C.c_int64), ("feat_stride_w", C.c_int64),
+        ("out_stride_n", C.c_int64), ("out_stride_c", C.c_int64), ("out_stride_h", C.c_int64), ("out_stride_w", C.c_int64),
+    ]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "stm_version": (C.c_int, []),
@@ -84,6 +94,7 @@ SIGNATURES = {
     "stm_correlation_fwd": (C.c_int, [C.POINTER(StmCorrDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "stm_correlation_backend": (C.c_int, [C.POINTER(StmCorrDesc)]),
+    "stm_roi_align_fwd": (C.c_int, [C.POINTER(StmRoiAlignDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "stm_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p]),
     "stm_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

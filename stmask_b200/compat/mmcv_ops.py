@@ -141,11 +141,9 @@ class ModulatedDeformConv2dPack(ModulatedDeformConv2d):
 
 
 def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode="avg", aligned=True):
-    """RoIAlign is a 'next' row, not part of this round's hot path: the import
-    the reference needs is satisfied with torchvision's CUDA kernel (library code, GPU only)."""
+    """mmcv.ops.roi_align as `bbox_feat_extractor` calls it (reference track_to_segment_head.py:85-86):
+    rois [n, 5] = (batch index, x1, y1, x2, y2) in feature-map pixels, average pooling.  Runs this library's
+    NHWC kernel (`stm_roi_align_fwd`); CUDA only, like every operator here."""
     if pool_mode != "avg":
         raise NotImplementedError("only pool_mode='avg' is available")
-    if not input.is_cuda:
-        raise RuntimeError("stmask_b200 operators run on CUDA only")
-    from torchvision.ops import roi_align as _tv_roi_align
-    return _tv_roi_align(input, rois, ops._pair(output_size), spatial_scale, sampling_ratio, aligned)
+    return ops.roi_align(input, rois, output_size, spatial_scale, sampling_ratio, aligned)

@@ -247,6 +247,19 @@ int stm_correlation_fwd(const StmCorrDesc* d, const void* x1, const void* x2, co
   return launch_corr_simt(*d, x1, x2, fa, fb, out, (cudaStream_t)stream);
 }
 
+int stm_roi_align_fwd(const StmRoiAlignDesc* d, const void* feat, const float* rois, void* out, void* stream) {
+  clear_error();
+  STM_CHECK_ARG(d != nullptr, "roi_align descriptor is null");
+  STM_CHECK_ARG(d->batch > 0 && d->h > 0 && d->w > 0 && d->c > 0, "bad feature map size");
+  STM_CHECK_ARG(d->n_rois >= 0 && d->pooled_h > 0 && d->pooled_w > 0, "bad roi count / output size");
+  STM_CHECK_ARG(dtype_ok(d->dtype) && dtype_ok(d->out_dtype), "unknown dtype");
+  STM_CHECK_ARG(d->feat_stride_w >= d->c, "NHWC pixel stride smaller than C");
+  STM_CHECK_ARG((int64_t)d->n_rois * d->pooled_h * d->pooled_w < (1ll << 31), "too many output bins");
+  if (d->n_rois == 0) return STM_OK;
+  STM_CHECK_ARG(feat && rois && out, "feat/rois/out pointer is null");
+  return launch_roi_align(*d, feat, rois, out, (cudaStream_t)stream);
+}
+
 int stm_nchw_to_nhwc(const void* src, int32_t sd, void* dst, int32_t dd, int32_t n, int32_t c, int32_t h, int32_t w,
                      void* stream) {
   clear_error();

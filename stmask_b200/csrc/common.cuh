@@ -108,5 +108,6 @@ int launch_corr_simt(const StmCorrDesc& d, const void* x1, const void* x2, const
 int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const void* fa, const void* fb, void* out,
                    cudaStream_t stream);
 bool corr_tc_supported(const StmCorrDesc& d, const char** why);
+int launch_roi_align(const StmRoiAlignDesc& d, const void* feat, const float* rois, void* out, cudaStream_t stream);
 
 }  // namespace stm

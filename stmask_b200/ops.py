@@ -543,6 +543,45 @@ def correlation_backend(shape: Sequence[int], dtype: torch.dtype, patch_size: in
 
 
 # --------------------------------------------------------------------------------------------
+# RoIAlign
+# --------------------------------------------------------------------------------------------
+def roi_align(input: torch.Tensor, rois: torch.Tensor, output_size=7, spatial_scale: float = 1.0, sampling_ratio: int = 0,
+              aligned: bool = True, channels_last: bool = True) -> torch.Tensor:
+    """mmcv.ops.roi_align (average pooling) on a CUDA feature map: input [B, C, H, W] (NHWC memory is consumed in
+    place), rois [n, 5] = (batch index, x1, y1, x2, y2) -> [n, C, ph, pw] (channels-last memory by default: the
+    TemporalNet convs that consume it want NHWC; reference track_to_segment_head.py:65-88)."""
+    _require_cuda(input, "input")
+    _require_cuda(rois, "rois")
+    if input.dim() != 4:
+        raise ValueError(f"input must be [B, C, H, W], got {tuple(input.shape)}")
+    if rois.dim() != 2 or rois.shape[1] != 5:
+        raise ValueError(f"rois must be [n, 5] = (batch index, x1, y1, x2, y2), got {tuple(rois.shape)}")
+    ph, pw = _pair(output_size)
+    if ph < 1 or pw < 1:
+        raise ValueError("output_size must be positive")
+    x = to_nhwc(input)
+    r = rois.to(torch.float32).contiguous()
+    b, c, h, w = x.shape
+    n = r.shape[0]
+    out = torch.empty((n, c, ph, pw), dtype=input.dtype, device=input.device,
+                      memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    if out.numel() == 0:
+        return out
+    d = L.StmRoiAlignDesc()
+    d.batch, d.h, d.w, d.c, d.n_rois = b, h, w, c, n
+    d.pooled_h, d.pooled_w = ph, pw
+    d.sampling_ratio, d.aligned = int(sampling_ratio), int(bool(aligned))
+    d.dtype = d.out_dtype = _dt(x, "input")
+    d.spatial_scale = float(spatial_scale)
+    d.feat_stride_n, d.feat_stride_h, d.feat_stride_w = x.stride(0), x.stride(2), x.stride(3)
+    d.out_stride_n, d.out_stride_c, d.out_stride_h, d.out_stride_w = out.stride()
+    with torch.cuda.device(input.device):
+        rc = L.lib().stm_roi_align_fwd(C.byref(d), x.data_ptr(), r.data_ptr(), out.data_ptr(), _stream(input))
+    L.check(rc, "stm_roi_align_fwd")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # torch.library registration (CUDA key only, fake impl for shape inference, no CPU key)
 # --------------------------------------------------------------------------------------------
 _op_cache = PackedWeightCache()

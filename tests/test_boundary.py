@@ -34,7 +34,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name)
     lib.stm_version.restype = ctypes.c_int
-    assert lib.stm_version() == 3
+    assert lib.stm_version() == 4
     lib.stm_last_error.restype = ctypes.c_char_p
     assert lib.stm_last_error() == b""
 

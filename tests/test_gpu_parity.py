@@ -440,6 +440,41 @@ def test_detections_after_fast_nms_match_the_reference(cuda_device, dtype):
         assert all(ref[p][0] == got[p][0] and abs(ref[p][1] - got[p][1]) <= 2e-2 for p in common)
 
 
+# ------------------------------------------------------------------------------------------
+# RoIAlign (the step right after the temporal-fusion concat)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_roi_align_vs_golden_and_oracle(cuda_device, dtype):
+    from mmcv.ops import roi_align                       # the drop-in the reference imports
+    ops = _ops()
+    z = load_golden("roi_align.npz")
+    feat = q(z["tv.feat"], dtype)
+    for name in ("a7", "a7_sr2", "l7", "a3x5_s05"):
+        ph, pw, scale, sr, al = z[f"tv.{name}.cfg"]
+        got = ops.roi_align(dev(feat, dtype, cuda_device), dev(z["tv.rois"], torch.float32, cuda_device), (int(ph), int(pw)),
+                            float(scale), int(sr), bool(al))
+        want = z[f"tv.{name}.y"] if dtype == torch.float32 else oracle.roi_align(feat, z["tv.rois"], (int(ph), int(pw)), float(scale), int(sr), bool(al))
+        assert got.shape == want.shape and rel_err(got.float().cpu().numpy(), want) <= TOL[dtype], name
+    # the reference's call site through the drop-in: roi_align(feature_maps, cat([box_ind, boxes]), 7), NCHW input
+    rois = np.concatenate([np.zeros((9, 1), np.float32), z["ref.boxes"]], 1)
+    f = q(z["ref.feat"], dtype)
+    got = roi_align(dev(f, dtype, cuda_device), dev(rois, torch.float32, cuda_device), 7)
+    want = z["ref.y"] if dtype == torch.float32 else oracle.roi_align(f, rois, 7)
+    assert rel_err(got.float().cpu().numpy(), want) <= TOL[dtype]
+    # on the padded 640-channel concat layout (channels-last, 16-byte vector path), many boxes, two images
+    rng = np.random.default_rng(5)
+    x = q(rng.standard_normal((2, 640, 24, 40)), dtype)
+    b = rng.random((64, 4)).astype(np.float32)
+    boxes = np.stack([b[:, 0] * 36, b[:, 1] * 20, b[:, 0] * 36 + 1 + b[:, 2] * 14, b[:, 1] * 20 + 1 + b[:, 3] * 10], 1)
+    rois = np.concatenate([rng.integers(0, 2, (64, 1)).astype(np.float32), boxes], 1).astype(np.float32)
+    got = ops.roi_align(dev(x, dtype, cuda_device, channels_last=True), dev(rois, torch.float32, cuda_device), 7)
+    assert got.stride(1) == 1 and rel_err(got.float().cpu().numpy(), oracle.roi_align(x, rois, 7)) <= TOL[dtype]
+    with pytest.raises(RuntimeError):
+        ops.roi_align(torch.zeros(1, 8, 4, 4), torch.zeros(1, 5))
+    with pytest.raises(ValueError):
+        ops.roi_align(dev(x, dtype, cuda_device), torch.zeros(3, 4, device=cuda_device))
+
+
 def test_correlation_pairs_reads_frames_and_halos_in_place(cuda_device):
     """Pair-indexed kernel (frames + received halos through index arrays) == the same kernel on gathered copies."""
     from stmask_b200 import sharding

@@ -1,5 +1,5 @@
 """Run ONE hot-path operator a few times (for ncu captures and quick timing).
-    python tools/profile_case.py fcb35|fcb33|fcb53|bb128s2|bb128|bb256|bb512s2|corr|corrpairs|corrsweep [--frames 72] [--reps 5] [--backend auto]
+    python tools/profile_case.py fcb35|fcb33|fcb53|bb128s2|bb128|bb256|bb512s2|corr|corrpairs|corrsweep|roialign [--frames 72] [--reps 5] [--backend auto]
 """
 import argparse
 import os
@@ -94,6 +94,17 @@ elif a.case == "corrpairs":      # the hot path's temporal fusion: (t-1, t) pair
     n = F - 1
     print("algorithmic (SURVEY 8d) GB/s = reported x", (633 + 512) / (633 + 1024.0))
     timeit(fn, nbytes=n * 960 * (633 + 2 * 256 + 2 * 256) * 2.0)
+elif a.case == "roialign":       # bbox_feat_extractor on the padded concat buffer: 100 boxes per frame pair, 7x7
+    n = F - 1
+    x = torch.randn(n, 640, 24, 40, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    nb = 100
+    g = torch.Generator(device=dev).manual_seed(0)
+    xy = torch.rand(n * nb, 2, device=dev, generator=g) * torch.tensor([30.0, 16.0], device=dev)
+    wh = 2 + torch.rand(n * nb, 2, device=dev, generator=g) * torch.tensor([10.0, 8.0], device=dev)
+    rois = torch.cat([torch.arange(n, device=dev).repeat_interleave(nb)[:, None].float(), xy, xy + wh], 1)
+    out = ops.roi_align(x, rois, 7)
+    # bytes: every output element written once + (per sample point) 4 corner vectors read; report output-side GB/s
+    timeit(lambda: ops.roi_align(x, rois, 7), nbytes=float(out.numel() * 2))
 elif a.case == "corrsweep":       # BASELINE.json configs[1]: batch 8 over P3..P7, plain cost volume
     lv = fpn_level_sizes()
     xs = [(torch.randn(8, 256, h, ww, device=dev).bfloat16().contiguous(memory_format=torch.channels_last),
