@@ -5,7 +5,7 @@
 //
 //   out[r, c, i, j] = mean over the gh x gw sample points of bin (i, j) of bilinear(feat[b_r, :, :, c], y, x)
 //
-// One CTA per (roi, output bin); threads across channels (channels-last => every corner of every sample point is
+// One CTA per (roi, output row); threads across (bin, 8-channel chunk) (channels-last => every corner of every sample point is
 // one contiguous C-vector: 16-byte loads when C % 8 == 0 in bf16, else element-wise), fp32 accumulation.
 // HBM/L2-bound by construction: every corner vector is read once per sample point; the maps are tiny (L2-resident).
 #include <type_traits>
@@ -53,11 +53,10 @@ __device__ __forceinline__ Corner4 corners(float y, float x, int H, int W, int64
 }
 
 template <typename T, typename OT, bool VEC8>
-__global__ void __launch_bounds__(128) roi_align_kernel(const RoiArgs a) {
+__global__ void __launch_bounds__(256) roi_align_kernel(const RoiArgs a) {
   const StmRoiAlignDesc& d = a.d;
-  const int bin = blockIdx.x % (d.pooled_h * d.pooled_w);
-  const int r = blockIdx.x / (d.pooled_h * d.pooled_w);
-  const int pi = bin / d.pooled_w, pj = bin - pi * d.pooled_w;
+  const int pi = blockIdx.x % d.pooled_h;          // one CTA per (roi, output row): pooled_w bins x channel chunks
+  const int r = blockIdx.x / d.pooled_h;
   const float* roi = a.rois + (size_t)r * 5;
   const int b = (int)roi[0];
   const float off = d.aligned ? 0.5f : 0.f;
@@ -71,9 +70,12 @@ __global__ void __launch_bounds__(128) roi_align_kernel(const RoiArgs a) {
   const float inv = 1.f / (float)max(gh * gw, 1);
   const bool b_ok = b >= 0 && b < d.batch;
   const T* img = reinterpret_cast<const T*>(a.feat) + (int64_t)(b_ok ? b : 0) * d.feat_stride_n;
-  OT* orow = reinterpret_cast<OT*>(a.out) + r * d.out_stride_n + pi * d.out_stride_h + pj * d.out_stride_w;
   constexpr int CPT = VEC8 ? 8 : 1;
-  for (int c0 = threadIdx.x * CPT; c0 < d.c; c0 += blockDim.x * CPT) {
+  const int chunks = (d.c + CPT - 1) / CPT;
+  const bool vec_store = VEC8 && sizeof(OT) == 2 && d.out_stride_c == 1 &&
+                         ((d.out_stride_n | d.out_stride_h | d.out_stride_w) & 7) == 0 && (((uintptr_t)a.out) & 15) == 0;
+  for (int item = threadIdx.x; item < d.pooled_w * chunks; item += blockDim.x) {
+    const int pj = item / chunks, c0 = (item - pj * chunks) * CPT;
     float acc[CPT];
 #pragma unroll
     for (int i = 0; i < CPT; ++i) acc[i] = 0.f;
@@ -84,10 +86,13 @@ __global__ void __launch_bounds__(128) roi_align_kernel(const RoiArgs a) {
         const Corner4 k = corners(yy, xx, d.h, d.w, d.feat_stride_h, d.feat_stride_w);
         if (!k.live) continue;
         if (VEC8) {
+          uint4 v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const uint4*>(img + k.o[q] + c0));
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float f[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(img + k.o[q] + c0)), f);
+            unpack8(v[q], f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = fmaf(k.w[q], f[i], acc[i]);
           }
@@ -97,19 +102,30 @@ __global__ void __launch_bounds__(128) roi_align_kernel(const RoiArgs a) {
         }
       }
     }
+    OT* orow = reinterpret_cast<OT*>(a.out) + r * d.out_stride_n + pi * d.out_stride_h + pj * d.out_stride_w;
+    if (VEC8 && vec_store) {
+      uint32_t w[4];
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) orow[(int64_t)(c0 + i) * d.out_stride_c] = from_f32<OT>(acc[i] * inv);
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * i] * inv, acc[2 * i + 1] * inv);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      *reinterpret_cast<uint4*>(orow + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) orow[(int64_t)(c0 + i) * d.out_stride_c] = from_f32<OT>(acc[i] * inv);
+    }
   }
 }
 
 template <typename T, typename OT>
 int launch_typed(const RoiArgs& args, cudaStream_t s) {
   const StmRoiAlignDesc& d = args.d;
-  const unsigned grid = (unsigned)(d.n_rois * d.pooled_h * d.pooled_w);
+  const unsigned grid = (unsigned)(d.n_rois * d.pooled_h);
   const bool vec8 = std::is_same<T, __nv_bfloat16>::value && (d.c & 7) == 0 && (((uintptr_t)args.feat) & 15) == 0 &&
                     ((d.feat_stride_n | d.feat_stride_h | d.feat_stride_w) & 7) == 0;
-  if (vec8) roi_align_kernel<T, OT, std::is_same<T, __nv_bfloat16>::value><<<grid, 128, 0, s>>>(args);
-  else roi_align_kernel<T, OT, false><<<grid, 128, 0, s>>>(args);
+  if (vec8) roi_align_kernel<T, OT, std::is_same<T, __nv_bfloat16>::value><<<grid, 256, 0, s>>>(args);
+  else roi_align_kernel<T, OT, false><<<grid, 256, 0, s>>>(args);
   count_launch();
   STM_CUDA_OK(cudaGetLastError());
   return STM_OK;
