@@ -40,3 +40,17 @@ def unpad_concat(x: torch.Tensor, patch_size: int = 11) -> torch.Tensor:
     consumers that have not been re-laid-out)."""
     pp, cp = patch_size * patch_size, padded_corr_channels(patch_size)
     return torch.cat([x[:, :pp], x[:, cp:]], dim=1)
+
+
+def pad_concat_weight(weight: torch.Tensor, patch_size: int = 11) -> torch.Tensor:
+    """Input-channel re-layout of a conv weight that consumes the concat (TemporalNet.conv1,
+    track_to_segment_head.py:10-37: [out, P*P + 2*Ct, kh, kw]) for the padded layout of `correlate_concat(padded=True)`:
+    zero input channels are inserted at [P*P, Cp), so conv(x_padded, pad_concat_weight(w)) == conv(x_reference, w)
+    exactly (the pad channels of x are zeros and meet zero weights).  Do it once, when the checkpoint is loaded."""
+    pp, cp = patch_size * patch_size, padded_corr_channels(patch_size)
+    if weight.dim() != 4 or weight.shape[1] <= pp:
+        raise ValueError(f"expected a [out, {pp} + 2*Ct, kh, kw] weight, got {tuple(weight.shape)}")
+    out = weight.new_zeros((weight.shape[0], weight.shape[1] + cp - pp) + tuple(weight.shape[2:]))
+    out[:, :pp] = weight[:, :pp]
+    out[:, cp:] = weight[:, pp:]
+    return out

@@ -107,3 +107,33 @@ def test_halo_exchange_world_size_2_gloo(mode, n_clips, fpc):
     assert all(ok for _, ok, _ in res), res
     n_halo = {"frame": n_clips, "clip": 1 if (n_clips, fpc) == (3, 5) else 0}[mode]
     assert res[1][2] == n_halo and res[0][2] == 0
+
+
+def test_padded_concat_layout_helpers_cpu():
+    """padded layout <-> reference layout: unpad_concat is the exact inverse, and a consumer conv with
+    pad_concat_weight gives the same result on the padded tensor as the original weight on the reference tensor."""
+    import torch.nn.functional as F
+    from stmask_b200.temporal_fusion import pad_concat_weight, padded_corr_channels, unpad_concat
+    assert padded_corr_channels(11) == 128 and padded_corr_channels(5) == 32 and padded_corr_channels(3) == 16
+    torch.manual_seed(0)
+    ref = torch.randn(2, 121 + 2 * 16, 7, 7)
+    padded = torch.zeros(2, 128 + 2 * 16, 7, 7)
+    padded[:, :121], padded[:, 128:] = ref[:, :121], ref[:, 121:]
+    assert torch.equal(unpad_concat(padded), ref)
+    w = torch.randn(8, 121 + 2 * 16, 3, 3)
+    assert torch.allclose(F.conv2d(padded, pad_concat_weight(w), padding=1), F.conv2d(ref, w, padding=1), atol=1e-5)
+    with pytest.raises(ValueError):
+        pad_concat_weight(torch.zeros(8, 100, 3, 3))
+
+
+def test_pair_index_tensors_match_pair_indices():
+    from stmask_b200.sharding import pair_index_tensors, pair_indices
+    for world, mode in ((1, "clip"), (2, "frame"), (4, "frame"), (2, "clip")):
+        plan = make_plan(3, 7, world, mode)
+        for r in range(world):
+            ri, ni = pair_index_tensors(plan, r, "cpu")
+            ref, nxt = pair_indices(plan, r)
+            assert ri.dtype == torch.int32 and ri.tolist() == ref and ni.tolist() == nxt
+            assert len(nxt) == plan.local_pairs(r)
+            n_local = plan.local_frames(r)
+            assert all(i < n_local for i in nxt) and sum(i >= n_local for i in ref) == len(plan.recv_halos(r))
