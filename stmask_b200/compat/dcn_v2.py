@@ -70,13 +70,36 @@ class DCN(DCNv2):
         self.conv_offset_mask.weight.data.zero_()
         self.conv_offset_mask.bias.data.zero_()
 
+    def _padded_predictor(self):
+        """conv_offset_mask's parameters with the output channels rounded up to a multiple of 8 (27 -> 32, zero
+        filters): cuDNN's channels-last kernels otherwise run an explicit channel-padding kernel before and after
+        every call.  Cached on the parameters' version counters; the module's parameters keep the original shapes
+        (checkpoint compatibility)."""
+        w, b = self.conv_offset_mask.weight, self.conv_offset_mask.bias
+        key = (w.data_ptr(), w._version, b.data_ptr(), b._version, w.dtype, w.device)
+        if getattr(self, "_pp_key", None) != key:
+            co = w.shape[0]
+            cp = (co + 7) // 8 * 8
+            wp = w.detach().new_zeros((cp,) + tuple(w.shape[1:]))
+            wp[:co] = w.detach()
+            bp = b.detach().new_zeros(cp)
+            bp[:co] = b.detach()
+            self._pp = (wp.contiguous(memory_format=torch.channels_last), bp)
+            self._pp_key = key
+        return self._pp
+
     def forward(self, input):
         # The original does chunk -> cat(o1, o2) -> sigmoid(mask) -> dcn_v2_conv; cat(o1, o2) is the
         # first 2/3 of the channels, so the kernel reads offsets and mask logits straight out of
         # `out` (views, no copies) and applies the sigmoid while sampling.
-        out = self.conv_offset_mask(input)     # regular conv: library plumbing
         n_off = 2 * self.deformable_groups * self.kernel_size[0] * self.kernel_size[1]
+        n_all = n_off + n_off // 2
+        if input.is_cuda and not torch.is_grad_enabled():
+            wp, bp = self._padded_predictor()
+            out = F.conv2d(input, wp, bp, self.stride, self.padding)     # regular conv: library plumbing (SURVEY.md §8f rank 2)
+        else:
+            out = self.conv_offset_mask(input)
         spec = self._spec()
-        return ops.deform_conv2d_multi([input], [out[:, :n_off]], [out[:, n_off:]],
+        return ops.deform_conv2d_multi([input], [out[:, :n_off]], [out[:, n_off:n_all]],
                                        self._cache.weight(self.weight, spec, input.dtype),
                                        self._cache.bias(self.bias), spec, mask_sigmoid=True)[0]
