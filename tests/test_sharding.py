@@ -137,3 +137,48 @@ def test_pair_index_tensors_match_pair_indices():
             assert len(nxt) == plan.local_pairs(r)
             n_local = plan.local_frames(r)
             assert all(i < n_local for i in nxt) and sum(i >= n_local for i in ref) == len(plan.recv_halos(r))
+
+
+def test_plans_cover_every_frame_once_property():
+    """Any (clips, frames per clip, world, mode): every frame has exactly one owner, segments of a clip are in rank
+    order and contiguous, halos sit exactly at the cuts between different owners, and the pair indices address the
+    previous frame of the same clip (locally, or through the matching received halo)."""
+    from hypothesis import given, settings, strategies as st
+    from stmask_b200.sharding import pair_indices
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 9), st.integers(1, 40), st.integers(1, 8), st.sampled_from(["clip", "frame"]))
+    def check(n_clips, fpc, world, mode):
+        plan = make_plan(n_clips, fpc, world, mode)
+        owner = {}
+        for r in range(world):
+            off = 0
+            for s in plan.segments[r]:
+                assert s.offset == off and s.length > 0
+                off += s.length
+                for f in range(s.start, s.stop):
+                    assert (s.clip, f) not in owner
+                    owner[(s.clip, f)] = (r, s.offset + f - s.start)
+            assert off == plan.local_frames(r)
+        assert len(owner) == n_clips * fpc
+        cuts = {(c, f) for c in range(n_clips) for f in range(1, fpc) if owner[(c, f)][0] != owner[(c, f - 1)][0]}
+        assert {(h.clip, h.frame) for h in plan.halos} == cuts
+        assert all(owner[(h.clip, h.frame)][0] == h.dst and owner[(h.clip, h.frame - 1)][0] == h.src for h in plan.halos)
+        if mode == "frame" and n_clips % world == 0:
+            counts = [plan.local_frames(r) for r in range(world)]
+            assert max(counts) - min(counts) <= max(1, n_clips // world) if fpc % world else max(counts) == min(counts)
+        for r in range(world):
+            ref, nxt = pair_indices(plan, r)
+            n_local = plan.local_frames(r)
+            recv = plan.recv_halos(r)
+            local = {v[1]: k for k, v in owner.items() if v[0] == r}
+            for a, b in zip(ref, nxt):
+                clip, f = local[b]
+                assert f > 0
+                if a < n_local:
+                    assert local[a] == (clip, f - 1)
+                else:
+                    assert (recv[a - n_local].clip, recv[a - n_local].frame) == (clip, f)
+            assert len(nxt) == plan.local_pairs(r) == sum(1 for (c, f), v in owner.items() if v[0] == r and f > 0)
+
+    check()
