@@ -45,7 +45,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define STM_ABI_VERSION 4
+#define STM_ABI_VERSION 5
 
 typedef enum StmStatus {
   STM_OK = 0,
@@ -75,7 +75,16 @@ typedef enum StmBackend {
 enum {
   STM_DCN_RELU = 1,          /* y = max(y, 0) in the epilogue (Featurealign.py:72)                  */
   STM_DCN_MASK_SIGMOID = 2,  /* mask holds logits; apply sigmoid while sampling (dcn_v2.DCN.forward) */
-  STM_DCN_ZERO_OFFSET = 4    /* offset == NULL: plain convolution through the same pipeline          */
+  STM_DCN_ZERO_OFFSET = 4,   /* offset == NULL: plain convolution through the same pipeline          */
+  /* Scheduling hints for the tcgen05 backend (results are identical; tests use them to force every CTA
+   * shape through the same entry point).  Stateless: they travel with the call, there are no
+   * environment variables or global knobs behind this ABI. */
+  STM_DCN_HINT_ROWS128 = 16, /* 128 output pixels per CTA (one accumulator)                          */
+  STM_DCN_HINT_ROWS256 = 32, /* 256 output pixels per CTA (two accumulators)                         */
+  STM_DCN_HINT_NO_PAIR = 64, /* do not pair CTAs (tcgen05 cta_group::1 only)                         */
+  STM_DCN_OUT_F32 = 128,     /* y is float32 [.., out_c] (strides in float elements) whatever conv->dtype:
+                                the offset / mask-logit predictor of a DCN keeps its fp32 accumulators   */
+  STM_DCN_HINT_DEEP_PIPE = 256 /* prefer more pipeline stages over L1 capacity                          */
 };
 
 /* Parameters shared by every problem of one call (one weight tensor). */
@@ -129,6 +138,13 @@ int stm_deform_conv2d_fwd(const StmDcnConv* conv, const StmDcnProblem* probs, in
 /* Which backend a call with these arguments would run: STM_BACKEND_SIMT / _TCGEN05,
  * or a negative StmStatus. */
 int stm_deform_conv2d_backend(const StmDcnConv* conv, const StmDcnProblem* probs, int32_t n_probs);
+
+/* Human-readable description of the kernel instantiation the call would launch on the current device
+ * ("simt", or "tcgen05 rows=256 n=256 ... pair=1 ..."), written NUL-terminated into buf[len].
+ * Parity tests assert it so that every benchmarked instantiation is known to have been compared
+ * with the oracle. */
+int stm_deform_conv2d_variant(const StmDcnConv* conv, const StmDcnProblem* probs, int32_t n_probs,
+                              char* buf, size_t len);
 
 /* FCB(ali) offsets from regressed box deltas (Featurealign.py:46-69), deform_groups = 1:
  *   shape[b, 0..3, h, w] = (t_x, t_y, t_w, t_h)

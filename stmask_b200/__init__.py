@@ -8,8 +8,11 @@ temporal-fusion hot path, behind the reference's own operator API.
     stmask_b200.temporal_fusion                     correlate, correlate_concat
     stmask_b200.backbone_dcn                        DCN placement rule + layer geometry
     stmask_b200.sharding                            clip/frame partition + one-frame halo exchange
+    stmask_b200.install_shims()                     make `dcn_v2`, `mmcv.ops`, `spatial_correlation_sampler` resolve here
 
 The arithmetic lives in stmask_b200/lib/libstmask_b200.so (C ABI: include/stmask_b200.h).
 There is no CPU path: importing works anywhere, calling an operator needs a B200.
 """
-__version__ = "0.1.0"
+__version__ = "0.2.0"
+
+from .shim_install import install_shims  # noqa: E402,F401

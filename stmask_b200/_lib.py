@@ -17,9 +17,11 @@ STM_F32, STM_BF16 = 0, 1
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
 BACKEND_NAMES = {BACKEND_AUTO: "auto", BACKEND_SIMT: "simt", BACKEND_TCGEN05: "tcgen05"}
 DCN_RELU, DCN_MASK_SIGMOID, DCN_ZERO_OFFSET = 1, 2, 4
+DCN_HINT_ROWS128, DCN_HINT_ROWS256, DCN_HINT_NO_PAIR = 16, 32, 64
+DCN_OUT_F32, DCN_HINT_DEEP_PIPE = 128, 256
 CORR_LEAKY_RELU, CORR_RELU, CORR_COPY_FEATS = 1, 2, 4
 DCN_MAX_PROBLEMS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class StmError(RuntimeError):
@@ -86,6 +88,7 @@ SIGNATURES = {
     "stm_deform_conv2d_fwd": (C.c_int, [C.POINTER(StmDcnConv), C.POINTER(StmDcnProblem), C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "stm_deform_conv2d_backend": (C.c_int, [C.POINTER(StmDcnConv), C.POINTER(StmDcnProblem), C.c_int32]),
+    "stm_deform_conv2d_variant": (C.c_int, [C.POINTER(StmDcnConv), C.POINTER(StmDcnProblem), C.c_int32, C.c_char_p, C.c_size_t]),
     "stm_fcb_ali_offsets": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.POINTER(C.c_int64),
                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "stm_fcb_ada_offsets": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.c_void_p,

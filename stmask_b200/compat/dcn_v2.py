@@ -10,7 +10,6 @@ import math
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import ops
 
@@ -51,6 +50,7 @@ class DCNv2(nn.Module):
         k = self.kernel_size[0] * self.kernel_size[1]
         if offset.shape[1] != 2 * self.deformable_groups * k or mask.shape[1] != self.deformable_groups * k:
             raise ValueError("offset/mask channel count does not match kernel_size and deformable_groups")
+        ops._no_grad_inputs(self.weight, self.bias)
         spec = self._spec()
         return ops.deform_conv2d_multi([input], [offset], [mask], self._cache.weight(self.weight, spec, input.dtype),
                                        self._cache.bias(self.bias), spec)[0]
@@ -65,40 +65,23 @@ class DCN(DCNv2):
         self.conv_offset_mask = nn.Conv2d(self.in_channels, channels_, kernel_size=self.kernel_size,
                                           stride=self.stride, padding=self.padding, bias=True)
         self.init_offset()
+        self._predictor = ops.PlainConv()
 
     def init_offset(self):
         self.conv_offset_mask.weight.data.zero_()
         self.conv_offset_mask.bias.data.zero_()
 
-    def _padded_predictor(self):
-        """conv_offset_mask's parameters with the output channels rounded up to a multiple of 8 (27 -> 32, zero
-        filters): cuDNN's channels-last kernels otherwise run an explicit channel-padding kernel before and after
-        every call.  Cached on the parameters' version counters; the module's parameters keep the original shapes
-        (checkpoint compatibility)."""
-        w, b = self.conv_offset_mask.weight, self.conv_offset_mask.bias
-        key = (w.data_ptr(), w._version, b.data_ptr(), b._version, w.dtype, w.device)
-        if getattr(self, "_pp_key", None) != key:
-            co = w.shape[0]
-            cp = (co + 7) // 8 * 8
-            wp = w.detach().new_zeros((cp,) + tuple(w.shape[1:]))
-            wp[:co] = w.detach()
-            bp = b.detach().new_zeros(cp)
-            bp[:co] = b.detach()
-            self._pp = (wp.contiguous(memory_format=torch.channels_last), bp)
-            self._pp_key = key
-        return self._pp
-
     def forward(self, input):
-        # The original does chunk -> cat(o1, o2) -> sigmoid(mask) -> dcn_v2_conv; cat(o1, o2) is the
-        # first 2/3 of the channels, so the kernel reads offsets and mask logits straight out of
-        # `out` (views, no copies) and applies the sigmoid while sampling.
+        # The original does conv_offset_mask -> chunk -> cat(o1, o2) -> sigmoid(mask) -> dcn_v2_conv.  Here the
+        # predictor is this library's own regular convolution (zero-offset mode of the same tcgen05 main loop)
+        # with the bias fused and the fp32 accumulators stored as fp32: sampling positions are never rounded to
+        # bf16.  cat(o1, o2) is the first 2/3 of its channels, so the sampling kernel reads offsets and mask logits
+        # straight out of that [B, Ho, Wo, 32] tensor (views, no copies) and applies the sigmoid while sampling.
+        ops._no_grad_inputs(input, self.weight, self.bias, self.conv_offset_mask.weight, self.conv_offset_mask.bias)
         n_off = 2 * self.deformable_groups * self.kernel_size[0] * self.kernel_size[1]
         n_all = n_off + n_off // 2
-        if input.is_cuda and not torch.is_grad_enabled():
-            wp, bp = self._padded_predictor()
-            out = F.conv2d(input, wp, bp, self.stride, self.padding)     # regular conv: library plumbing (SURVEY.md §8f rank 2)
-        else:
-            out = self.conv_offset_mask(input)
+        com = self.conv_offset_mask
+        out = self._predictor([input], com.weight, com.bias, com.stride, com.padding, com.dilation, out_f32=True)[0]
         spec = self._spec()
         return ops.deform_conv2d_multi([input], [out[:, :n_off]], [out[:, n_off:n_all]],
                                        self._cache.weight(self.weight, spec, input.dtype),

@@ -68,6 +68,7 @@ class DeformConv2d(nn.Module):
         # already reads zeros here, so the result is identical without the extra copies.
         if x.dim() != 4:
             raise ValueError(f"Expected 4D tensor as input, got {x.dim()}D tensor instead.")
+        ops._no_grad_inputs(self.weight)
         spec = self.spec()
         return ops.deform_conv2d_multi([x], [offset], None, self._cache.weight(self.weight, spec, x.dtype), None, spec,
                                        relu=relu)[0]
@@ -120,6 +121,7 @@ class ModulatedDeformConv2d(nn.Module):
                             self.dilation, self.groups, self.deform_groups)
 
     def forward(self, x, offset, mask, mask_sigmoid=False):
+        ops._no_grad_inputs(self.weight, self.bias)
         spec = self.spec()
         return ops.deform_conv2d_multi([x], [offset], [mask], self._cache.weight(self.weight, spec, x.dtype),
                                        self._cache.bias(self.bias), spec, mask_sigmoid=mask_sigmoid)[0]

@@ -21,6 +21,31 @@ void set_error(const char* fmt, ...) {
 void clear_error() { g_err[0] = 0; }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+int current_device_ordinal() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1;
+  }
+  return dev;
+}
+
+int device_sm_count() {
+  static std::atomic<int> cache[64];
+  const int dev = current_device_ordinal();
+  if (dev >= 0 && dev < 64) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  int n = 0;
+  if (dev < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    return 148;
+  }
+  if (dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
+
 int pack_weight_ohwi(const void* src, int sd, void* dst, int dd, int O, int I, int K, cudaStream_t stream);
 int transpose_batched(const void* src, int sd, void* dst, int dd, int n, int rows, int cols, cudaStream_t stream);
 int ali_offsets(const void* shape, const int64_t* ss, int sd, void* off, const int64_t* os, int od, int B, int H, int W,
@@ -181,6 +206,25 @@ int stm_deform_conv2d_backend(const StmDcnConv* c, const StmDcnProblem* pr, int3
   rc = validate_problems(c, pr, n);
   if (rc != STM_OK) return rc;
   return pick_dcn_backend(c, pr, n);
+}
+
+int stm_deform_conv2d_variant(const StmDcnConv* c, const StmDcnProblem* pr, int32_t n, char* buf, size_t len) {
+  clear_error();
+  STM_CHECK_ARG(buf != nullptr && len > 0, "variant buffer is null");
+  buf[0] = 0;
+  int rc = validate_conv(c);
+  if (rc != STM_OK) return rc;
+  rc = validate_problems(c, pr, n);
+  if (rc != STM_OK) return rc;
+  // the plan is a function of the arguments (and the SM count) alone: it also answers without a driver
+  const char* why = "";
+  const bool tc = c->backend != STM_BACKEND_SIMT && dcn_tc_shape_supported(c, pr, n, &why);
+  if (!tc && c->backend == STM_BACKEND_TCGEN05) { set_error("tcgen05 deformable conv not available for this call: %s", why); return STM_ERR_UNSUPPORTED; }
+  if (!tc) { snprintf(buf, len, "simt"); return STM_OK; }
+  DcnParams p;
+  fill_params(c, pr, n, nullptr, nullptr, &p);
+  if (p.n_probs == 0) { snprintf(buf, len, "empty"); return STM_OK; }
+  return dcn_tc_variant(c, p, buf, len);
 }
 
 int stm_deform_conv2d_fwd(const StmDcnConv* c, const StmDcnProblem* pr, int32_t n, const void* w_packed, const float* bias,

@@ -15,6 +15,16 @@ void set_error(const char* fmt, ...);
 void clear_error();
 void count_launch(int n = 1);
 
+// SM count of the CURRENT device (cached per device ordinal; thread-safe).
+int device_sm_count();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember, per device
+// ordinal, the largest value already set for one kernel instantiation (one cache object per instantiation).
+struct SmemAttrCache {
+  int v[64];
+};
+int current_device_ordinal();
+
 #define STM_CHECK_ARG(cond, ...)                 \
   do {                                           \
     if (!(cond)) {                               \
@@ -97,11 +107,23 @@ __device__ __forceinline__ Sample4 make_sample(float h, float w, int H, int W, i
   return s;
 }
 
+template <typename K>
+int ensure_dynamic_smem(K kernel, int bytes, SmemAttrCache& cache) {
+  const int dev = current_device_ordinal();
+  if (dev < 0 || dev >= 64 || __atomic_load_n(&cache.v[dev], __ATOMIC_ACQUIRE) < bytes) {
+    STM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (dev >= 0 && dev < 64) __atomic_store_n(&cache.v[dev], bytes, __ATOMIC_RELEASE);
+  }
+  return STM_OK;
+}
+
 // host-side launchers implemented in the .cu files
 int launch_dcn_simt(const DcnParams& p, int dtype, int offset_dtype, cudaStream_t stream);
 int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p, void* workspace, size_t ws_bytes, cudaStream_t stream);
 bool dcn_tc_supported(const StmDcnConv* conv, const StmDcnProblem* probs, int n, const char** why);
+bool dcn_tc_shape_supported(const StmDcnConv* conv, const StmDcnProblem* probs, int n, const char** why);
 size_t dcn_tc_workspace(const StmDcnConv* conv, const StmDcnProblem* probs, int n);
+int dcn_tc_variant(const StmDcnConv* conv, const DcnParams& p, char* buf, size_t len);
 
 int launch_corr_simt(const StmCorrDesc& d, const void* x1, const void* x2, const void* fa, const void* fb, void* out,
                      cudaStream_t stream);

@@ -460,26 +460,14 @@ int encode_nhwc_map(CUtensorMap* m, const void* ptr, int c, int w, int h, int b,
   return STM_OK;
 }
 
-int sm_count_corr() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
-      (void)cudaGetLastError();
-      n = 148;
-    }
-  }
-  return n;
-}
+SmemAttrCache g_corr_smem_attr[12];    // one per instantiation (out dtype x tile width x post-op)
 
 template <typename OT, int TW, int POST>
 int launch_t(const CorrTcArgs& args, const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& m1a, int grid, int smem_bytes,
              cudaStream_t stream) {
-  static int configured = 0;
-  if (configured < smem_bytes) {
-    STM_CUDA_OK(cudaFuncSetAttribute(corr_tc_kernel<OT, TW, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = smem_bytes;
-  }
+  constexpr int slot = (sizeof(OT) == 4 ? 6 : 0) + (TW == 20 ? 3 : 0) + POST;
+  const int rc = ensure_dynamic_smem(corr_tc_kernel<OT, TW, POST>, smem_bytes, g_corr_smem_attr[slot]);
+  if (rc != STM_OK) return rc;
   corr_tc_kernel<OT, TW, POST><<<grid, NUM_THREADS, smem_bytes, stream>>>(args, m1, m2, m1a);
   count_launch();
   STM_CUDA_OK(cudaGetLastError());
@@ -514,16 +502,18 @@ bool corr_tc_supported(const StmCorrDesc& d, const char** why) {
       (d.batch > 1 && (d.x1_stride_n <= 0 || d.x2_stride_n <= 0))) { *why = "non-positive strides"; return false; }
   if (d.batch < 1) { *why = "empty batch"; return false; }
   if (get_tensormap_encoder() == nullptr) { *why = "cuTensorMapEncodeTiled unavailable"; return false; }
-  if (const char* e = getenv("STM_CORR_FORCE_SIMT")) {
-    if (atoi(e) != 0) { *why = "STM_CORR_FORCE_SIMT"; return false; }
-  }
   return true;
 }
 
 int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const void* fa, const void* fb, void* out,
                    cudaStream_t stream) {
   if (((uintptr_t)x1 & 15) || ((uintptr_t)x2 & 15)) {
-    // descriptors need 16-byte aligned bases; rare (sliced tensors) -> CUDA-core kernel
+    // descriptors need 16-byte aligned bases; rare (sliced tensors) -> CUDA-core kernel, which knows nothing
+    // about pair indexing
+    if (d.x1_index != nullptr) {
+      set_error("pair-indexed correlation needs 16-byte aligned x1 / x2 (tcgen05 backend only)");
+      return STM_ERR_UNSUPPORTED;
+    }
     return launch_corr_simt(d, x1, x2, fa, fb, out, stream);
   }
   CorrTcArgs args;
@@ -531,18 +521,16 @@ int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const v
   args.fa = fa; args.fb = fb; args.out = out;
   args.trace = nullptr;
   args.l2_prefetch = 1;
+#ifdef STM_DCN_EXPERIMENTS   // profiling builds only (tools/corr_trace.py); the product library has no environment knobs
   if (const char* e = getenv("STM_CORR_L2PF")) args.l2_prefetch = atoi(e);
   if (const char* e = getenv("STM_DEBUG_BUF")) args.trace = reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0));
+#endif
   const int P = d.patch, dl = d.dilation_patch;
   // tile shape: fewest tiles wins (6x20 tiles a 24x40 map exactly: 8 tiles instead of 9); ties -> 8x16
   int tw = 16, th = 8;
   {
     const int t816 = tiles_per_image(d, 8, 16), t620 = tiles_per_image(d, 6, 20);
     if (t620 < t816) { tw = 20; th = 6; }
-    if (const char* e = getenv("STM_CORR_TW")) {           // tuning knob (profiling runs)
-      const int v = atoi(e);
-      if (v == 16) { tw = 16; th = 8; } else if (v == 20) { tw = 20; th = 6; }
-    }
   }
   args.th = th;
   args.rh = th + P - 1;
@@ -596,7 +584,7 @@ int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const v
                          d.alt_frames > 1 ? d.x1_alt_stride_n : (int64_t)d.h * d.x1_alt_stride_h, tw, th, dl);
     if (rc != STM_OK) return rc;
   }
-  const int grid = args.n_tiles < sm_count_corr() ? args.n_tiles : sm_count_corr();
+  const int grid = args.n_tiles < device_sm_count() ? args.n_tiles : device_sm_count();
   const int post = (d.flags & STM_CORR_RELU) ? 2 : ((d.flags & STM_CORR_LEAKY_RELU) ? 1 : 0);
 #define STM_CORR_LAUNCH(OT_, TW_)                                                                     \
   do {                                                                                                \

@@ -168,7 +168,9 @@ __global__ void __launch_bounds__(NT) dcn_simt_kernel(const __grid_constant__ Dc
 
   // ---- epilogue: bias, ReLU, store NHWC ----
   T* __restrict__ y = reinterpret_cast<T*>(pr.y);
+  float* __restrict__ yf = reinterpret_cast<float*>(pr.y);
   const bool relu = (p.flags & STM_DCN_RELU) != 0;
+  const bool out_f32 = (p.flags & STM_DCN_OUT_F32) != 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t yb = pix_ybase[tm * 4 + i];
@@ -180,7 +182,8 @@ __global__ void __launch_bounds__(NT) dcn_simt_kernel(const __grid_constant__ Dc
       float v = acc[i][j];
       if (p.bias != nullptr) v += p.bias[oc];
       if (relu) v = fmaxf(v, 0.f);
-      y[yb + oc] = from_f32<T>(v);
+      if (out_f32) yf[yb + oc] = v;
+      else y[yb + oc] = from_f32<T>(v);
     }
   }
 }

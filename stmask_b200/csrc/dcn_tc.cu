@@ -20,7 +20,7 @@
 //
 // Replaces modulated_deformable_im2col + per-sample SGEMM of dcn_v2 / mmcv (reference
 // backbone.py:45, Featurealign.py:72).
-#include <cstdlib>
+#include <cstdio>
 #include <mutex>
 
 #include "common.cuh"
@@ -54,6 +54,7 @@ constexpr int MAX_STAGES = 6;
 constexpr int META_BUFS = 3;            // sample metadata is computed one tap ahead of the gather that reads it
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int ZERO_PAGE_BYTES = 4096;   // >= 2 * in_c (dcn_tc_supported caps in_c at 2048)
+constexpr int FLAG_OFFSETS_BF16 = 1 << 16;   // internal (set by the launcher): offsets / masks are stored as bf16
 
 // Corners that carry no weight (outside the map, outside the sample's support, rows past the end of the
 // problem) are pointed here instead of being predicated off: the gather stays branch-free and 0 * 0 = 0,
@@ -72,8 +73,9 @@ template <int M_TILES>
 struct SmemLayout {
   static constexpr int ROWS = TILE_M * M_TILES;
   int stage_bytes, meta_p, meta_w, bars, total;
-  __host__ __device__ SmemLayout(int block_n, int stages) {
-    stage_bytes = M_TILES * A_TILE_BYTES + block_n * 128;
+  // pair: each CTA of a cta_group::2 pair holds only its half of the N tile's weight rows
+  __host__ __device__ SmemLayout(int block_n, int stages, bool pair) {
+    stage_bytes = M_TILES * A_TILE_BYTES + (pair ? block_n / 2 : block_n) * 128;
     int off = stages * stage_bytes;
     meta_p = off; off += META_BUFS * ROWS * 32;    // four 64-bit corner pointers per row
     meta_w = off; off += META_BUFS * ROWS * 8;     // four bf16 corner weights per row
@@ -94,11 +96,25 @@ __device__ __forceinline__ uint64_t add_wide(uint32_t lo, uint32_t hi, uint32_t 
   return r;
 }
 
-// PW producer warps (8 or 16) + 1 TMA warp + 1 MMA warp.  CFENCE: the generic->async proxy fence for the
-// A tile is executed by the MMA thread after it has acquired the stage (instead of by every producer
-// thread before its release): a producer-side fence.proxy.async compiles to MEMBAR.ALL.CTA, which also
-// waits for the gather loads that are already in flight for the NEXT K block and drains the pipeline.
-template <int M_TILES, int PW, int D, bool CFENCE>
+// PW producer warps (8 or 16) + 1 TMA warp + 1 MMA warp.  The generic->async proxy fence for the A tile is
+// executed by the MMA thread after it has acquired the stage (instead of by every producer thread before its
+// release): a producer-side fence.proxy.async compiles to MEMBAR.ALL.CTA, which also waits for the gather
+// loads that are already in flight for the NEXT K block and drains the pipeline.
+//
+// PAIR: two CTAs of a cluster (same TPC) work as ONE tcgen05 cta_group::2 unit.  Each CTA gathers the A tile of
+// its own ROWS output pixels and loads only HALF of the N-tile's weight rows; the leader's MMA (M = 256: 128
+// TMEM lanes in each CTA) reads both halves.  Per CTA that halves the weight bytes fetched from L2 and the
+// shared-memory bytes the tensor core reads for the B operand (B is 2/3 of the operand traffic at N = 256) —
+// the shared-memory/L1 data pipe is what bounds this kernel (gather loads, A-tile stores and UMMA operand
+// reads all go through it).  Synchronisation: the producer warps and the weight TMA of BOTH CTAs arrive on the
+// LEADER's full barrier (remote mbarrier arrive / complete_tx), the leader's tcgen05.commit multicasts to the
+// empty barriers of both CTAs.
+//
+// PLAIN: zero offsets (STM_DCN_ZERO_OFFSET): the sample is the pixel itself, so a gather task is ONE 16-byte
+// load and a store (no blend) and the metadata is one pointer per row.  This is the regular convolution that
+// predicts a DCN's offsets / mask logits (backbone.py:24-26) and the TemporalNet convs
+// (track_to_segment_head.py:14-16) on the same tcgen05 main loop.
+template <int M_TILES, int PW, int D, bool PAIR, bool PLAIN>
 __global__ void __launch_bounds__(PW * 32 + 64, (M_TILES == 1 && PW == 8) ? 2 : 1)
 dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap tmap_w) {
   constexpr int ROWS = TILE_M * M_TILES;
@@ -106,11 +122,13 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   constexpr int ROWS_PER_PASS = PW * 4;                 // rows covered by one sweep of the producer warps
   constexpr int TPK = ROWS / ROWS_PER_PASS;             // gather tasks per thread per K block
   constexpr int CPT = 4 * ROWS / PT;                    // corners per thread when computing sample metadata
+  constexpr int NC = PLAIN ? 1 : 4;                     // corner loads per gather task
   static_assert(CPT == 1 || CPT == 2 || CPT == 4, "metadata split");
   static_assert(D >= 1 && D <= TPK && TPK % D == 0, "gather look-ahead must divide the tasks per K block");
+  static_assert(!PAIR || !(M_TILES == 1 && PW == 8), "CTA pairs run one CTA per SM");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SmemLayout<M_TILES> L(a.block_n, a.stages);
+  const SmemLayout<M_TILES> L(a.block_n, a.stages, PAIR);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* accum_bar = empty_bar + MAX_STAGES;
@@ -121,8 +139,10 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   const int warp = tid >> 5, lane = tid & 31;
   const int block_n = a.block_n, stages = a.stages;
   const int n0 = blockIdx.y * block_n;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
 
-  // ---- which feature map does this M block belong to? ----
+  // ---- which feature map does this M block belong to?  (a pair's odd filler CTA past the last tile owns no rows) ----
   int pi = 0;
 #pragma unroll 1
   for (int i = 1; i < p.n_probs; ++i)
@@ -134,20 +154,23 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   if (warp == PW && lane == 0) {
     prefetch_tensormap(&tmap_w);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], PW + 1);               // producer warps + the TMA thread's expect_tx arrive
+      // producer warps (of both CTAs of a pair) + the (leader's) TMA thread's expect_tx arrive
+      mbar_init(&full_bar[s], PAIR ? 2 * PW + 1 : PW + 1);
       mbar_init(&empty_bar[s], 1);                   // tcgen05.commit
     }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
   if (warp == PW + 1) {
-    tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(tmem_slot, (uint32_t)a.tmem_cols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols); tmem_relinquish(); }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // the leader's full barriers as seen from this CTA
+  const uint32_t full_leader = PAIR ? map_to_cta(smem_u32(full_bar), 0u) : smem_u32(full_bar);
 
   const int K = p.kh * p.kw;
   const int cpd = p.in_c / p.dg;            // channels per deformable group (multiple of 64)
@@ -166,8 +189,8 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
 
     // ---- sample metadata: thread -> (row, CPT of its 4 corners) ----
     const int mrow = tid % ROWS, cg = tid / ROWS;
-    const bool has_off = pr.offset != nullptr, has_mask = pr.mask != nullptr;
-    const bool off_bf16 = (p.flags & 0x100) != 0;      // internal flag: offsets/masks stored as bf16
+    const bool has_off = !PLAIN && pr.offset != nullptr, has_mask = !PLAIN && pr.mask != nullptr;
+    const bool off_bf16 = (p.flags & FLAG_OFFSETS_BF16) != 0;      // internal flag: offsets/masks stored as bf16
     const bool mask_sig = has_mask && (p.flags & STM_DCN_MASK_SIGMOID);
     int hb = 0, wb = 0;                     // top-left of the un-deformed receptive field
     bool rvalid = false;
@@ -193,7 +216,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     // raw (dy, dx, mask) of this thread's row for iteration `it`; issued one iteration ahead of its use
     auto load_raw = [&](int it_, float& oy, float& ox, float& mk) {
       oy = 0.f; ox = 0.f; mk = 1.f;
-      if (!rvalid || it_ >= n_iter) return;
+      if (PLAIN || !rvalid || it_ >= n_iter) return;
       const int tap_ = it_ / p.dg, g_ = it_ - tap_ * p.dg;
       if (has_off) {
         const int64_t o = off_base + (int64_t)(g_ * 2 * K + 2 * tap_) * pr.off_sc;
@@ -216,6 +239,16 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       const int buf = it_ % META_BUFS;
       const int tap_ = it_ / p.dg, g_ = it_ - tap_ * p.dg;
       const int ti = tap_ / p.kw, tj = tap_ - ti * p.kw;
+      if (PLAIN) {
+        // regular convolution: the tap's pixel itself, or the zero page when it lies in the padding
+        if (cg == 0) {
+          const int yy = hb + ti * p.dh, xx = wb + tj * p.dw;
+          const bool ok = rvalid && yy >= 0 && yy < pr.in_h && xx >= 0 && xx < pr.in_w;
+          const uint64_t ptr = ok ? reinterpret_cast<uint64_t>(ximg + ((int64_t)yy * pr.x_sh + (int64_t)xx * pr.x_sw + g_ * cpd)) : zero_page;
+          *reinterpret_cast<uint2*>(smem + L.meta_p + (buf * ROWS + mrow) * 32) = make_uint2((uint32_t)ptr, (uint32_t)(ptr >> 32));
+        }
+        return;
+      }
       const float h = (float)(hb + ti * p.dh) + oy;
       const float w = (float)(wb + tj * p.dw) + ox;
       const bool inside = rvalid && h > -1.f && w > -1.f && h < (float)pr.in_h && w < (float)pr.in_w;
@@ -240,7 +273,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       uint8_t* mpd = smem + L.meta_p + ((buf * ROWS + mrow) * 32 + cg * CPT * 8);
       uint8_t* mwd = smem + L.meta_w + ((buf * ROWS + mrow) * 8 + cg * CPT * 2);
       if (CPT == 4) {
-        reinterpret_cast<uint4*>(mpd)[0] = make_uint4((uint32_t)ptr[0], (uint32_t)(ptr[0] >> 32), (uint32_t)ptr[1], (uint32_t)(ptr[1] >> 32));
+        reinterpret_cast<uint4*>(mpd)[0] = make_uint4((uint32_t)ptr[0], (uint32_t)(ptr[0] >> 32), (uint32_t)ptr[1 % CPT], (uint32_t)(ptr[1 % CPT] >> 32));
         reinterpret_cast<uint4*>(mpd)[1] = make_uint4((uint32_t)ptr[2 % CPT], (uint32_t)(ptr[2 % CPT] >> 32), (uint32_t)ptr[3 % CPT], (uint32_t)(ptr[3 % CPT] >> 32));
         *reinterpret_cast<uint2*>(mwd) = make_uint2(wt[0] | (wt[1 % CPT] << 16), wt[2 % CPT] | (wt[3 % CPT] << 16));
       } else if (CPT == 2) {
@@ -253,11 +286,11 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     };
 
     // One gather task = (row, 8 channels) of one K block: 4 corner loads, fp32 blend (FHFMA.BF16: bf16 data and
-    // weights feed the FMA directly), one rounding to bf16, one 16-byte store.  Every thread keeps the TPK
-    // tasks of the NEXT K block in flight while it blends and stores the current one.
+    // weights feed the FMA directly), one rounding to bf16, one 16-byte store (PLAIN: one load, one store).  Every
+    // thread keeps D tasks in flight while it blends and stores the current one.
     struct GTask {
       uint32_t w01, w23;   // bf16 corner weights (w0 | w1 << 16, w2 | w3 << 16)
-      uint4 c[4];
+      uint4 c[NC];
     };
     struct GMeta {
       uint4 p01, p23;
@@ -265,43 +298,53 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     };
     auto read_meta = [&](GMeta& m, int buf, int j) {
       const uint32_t pa = mp_addr + (uint32_t)((buf * ROWS + j * ROWS_PER_PASS) * 32);
+      if (PLAIN) {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(m.p01.x), "=r"(m.p01.y) : "r"(pa));
+        return;
+      }
       const uint32_t wa = mw_addr + (uint32_t)((buf * ROWS + j * ROWS_PER_PASS) * 8);
       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m.p01.x), "=r"(m.p01.y), "=r"(m.p01.z), "=r"(m.p01.w) : "r"(pa));
       asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m.p23.x), "=r"(m.p23.y), "=r"(m.p23.z), "=r"(m.p23.w) : "r"(pa + 16u));
       asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(m.w.x), "=r"(m.w.y) : "r"(wa));
     };
     auto issue = [&](GTask& t, const GMeta& m, uint32_t coff) {
-      t.w01 = m.w.x; t.w23 = m.w.y;
       t.c[0] = ldg_nc_v4(add_wide(m.p01.x, m.p01.y, coff));
-      t.c[1] = ldg_nc_v4(add_wide(m.p01.z, m.p01.w, coff));
-      t.c[2] = ldg_nc_v4(add_wide(m.p23.x, m.p23.y, coff));
-      t.c[3] = ldg_nc_v4(add_wide(m.p23.z, m.p23.w, coff));
+      if (!PLAIN) {
+        t.w01 = m.w.x; t.w23 = m.w.y;
+        t.c[1 % NC] = ldg_nc_v4(add_wide(m.p01.z, m.p01.w, coff));
+        t.c[2 % NC] = ldg_nc_v4(add_wide(m.p23.x, m.p23.y, coff));
+        t.c[3 % NC] = ldg_nc_v4(add_wide(m.p23.z, m.p23.w, coff));
+      }
     };
     auto finish = [&](const GTask& t, uint32_t dst) {
-      const uint32_t* q0 = reinterpret_cast<const uint32_t*>(&t.c[0]);
-      const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&t.c[1]);
-      const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&t.c[2]);
-      const uint32_t* q3 = reinterpret_cast<const uint32_t*>(&t.c[3]);
-      uint16_t w0, w1, w2, w3;
-      split16(t.w01, w0, w1);
-      split16(t.w23, w2, w3);
       uint32_t o[4];
+      if (PLAIN) {
+        o[0] = t.c[0].x; o[1] = t.c[0].y; o[2] = t.c[0].z; o[3] = t.c[0].w;
+      } else {
+        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(&t.c[0]);
+        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&t.c[1 % NC]);
+        const uint32_t* q2 = reinterpret_cast<const uint32_t*>(&t.c[2 % NC]);
+        const uint32_t* q3 = reinterpret_cast<const uint32_t*>(&t.c[3 % NC]);
+        uint16_t w0, w1, w2, w3;
+        split16(t.w01, w0, w1);
+        split16(t.w23, w2, w3);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint16_t a0, a1, b0, b1, c0, c1, d0, d1;
-        split16(q0[i], a0, a1);
-        split16(q1[i], b0, b1);
-        split16(q2[i], c0, c1);
-        split16(q3[i], d0, d1);
-        float lo = fma_bf16(a0, w0, 0.f);
-        float hi = fma_bf16(a1, w0, 0.f);
-        lo = fma_bf16(b0, w1, lo);
-        hi = fma_bf16(b1, w1, hi);
-        lo = fma_bf16(c0, w2, lo);
-        hi = fma_bf16(c1, w2, hi);
-        lo = fma_bf16(d0, w3, lo);
-        hi = fma_bf16(d1, w3, hi);
-        o[i] = pack_bf16(lo, hi);
+        for (int i = 0; i < 4; ++i) {
+          uint16_t a0, a1, b0, b1, c0, c1, d0, d1;
+          split16(q0[i], a0, a1);
+          split16(q1[i], b0, b1);
+          split16(q2[i], c0, c1);
+          split16(q3[i], d0, d1);
+          float lo = fma_bf16(a0, w0, 0.f);
+          float hi = fma_bf16(a1, w0, 0.f);
+          lo = fma_bf16(b0, w1, lo);
+          hi = fma_bf16(b1, w1, hi);
+          lo = fma_bf16(c0, w2, lo);
+          hi = fma_bf16(c1, w2, hi);
+          lo = fma_bf16(d0, w3, lo);
+          hi = fma_bf16(d1, w3, hi);
+          o[i] = pack_bf16(lo, hi);
+        }
       }
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]));
     };
@@ -358,9 +401,11 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
         if (j + 1 < TPK) m = mn;
       }
       // this warp's part of the A tile of `stage` is complete
-      if (!CFENCE) fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(full_leader + (uint32_t)stage * 8u);
+        else mbar_arrive(&full_bar[stage]);
+      }
       if (++stage == stages) { stage = 0; phase ^= 1u; }
       it = nit; cc = ncc;
     }
@@ -389,28 +434,30 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       const int ho = r / pr.out_w, wo = r - ho * pr.out_w;
       yoff = b * pr.y_sn + ho * pr.y_sh + wo * pr.y_sw;
     }
-    __nv_bfloat16* yrow = reinterpret_cast<__nv_bfloat16*>(pr.y) + yoff + n0;
     const bool relu = (p.flags & STM_DCN_RELU) != 0;
+    const bool out_f32 = (p.flags & STM_DCN_OUT_F32) != 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * block_n);
     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
       uint32_t acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
       tmem_ld_wait();
       if (row_ok) {
-        uint32_t o[8];
+        float f[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float lo = __uint_as_float(acc[2 * i]), hi = __uint_as_float(acc[2 * i + 1]);
-          if (p.bias != nullptr) {
-            lo += __ldg(p.bias + n0 + c0 + 2 * i);
-            hi += __ldg(p.bias + n0 + c0 + 2 * i + 1);
-          }
-          if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-          o[i] = pack_bf16(lo, hi);
+        for (int i = 0; i < 16; ++i) {
+          f[i] = __uint_as_float(acc[i]);
+          if (p.bias != nullptr) f[i] += __ldg(p.bias + n0 + c0 + i);
+          if (relu) f[i] = fmaxf(f[i], 0.f);
         }
-        uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
-        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        if (out_f32) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(pr.y) + yoff + n0 + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pr.y) + yoff + n0 + c0);
+          dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+        }
       }
     }
   } else if (warp == PW) {
@@ -418,6 +465,8 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     if (lane == 0) {
       int s = 0;
       uint32_t phase = 0;
+      // a pair splits the N tile: this CTA loads weight rows [n0 + rank * block_n/2, + block_n/2)
+      const int nrow0 = PAIR ? n0 + (int)cta_rank * (block_n / 2) : n0;
 #pragma unroll 1
       for (int tap = 0; tap < K; ++tap)
 #pragma unroll 1
@@ -425,22 +474,33 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
 #pragma unroll 1
           for (int cc = 0; cc < chunks; ++cc) {
             mbar_wait_relaxed(&empty_bar[s], phase ^ 1u);
-            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(block_n * 128));
-            tma_load_2d(smem + s * L.stage_bytes + M_TILES * A_TILE_BYTES, &tmap_w, &full_bar[s],
-                        tap * p.in_c + g * cpd + cc * BLOCK_K, n0);
+            uint8_t* dst = smem + s * L.stage_bytes + M_TILES * A_TILE_BYTES;
+            const int kcol = tap * p.in_c + g * cpd + cc * BLOCK_K;
+            if (PAIR) {
+              if (leader) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(block_n * 128));     // both halves
+              tma_load_2d_pair(dst, &tmap_w, full_leader + (uint32_t)s * 8u, kcol, nrow0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(block_n * 128));
+              tma_load_2d(dst, &tmap_w, &full_bar[s], kcol, nrow0);
+            }
             if (++s == stages) { s = 0; phase ^= 1u; }
           }
     }
   } else {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(TILE_M, (uint32_t)block_n);
+    // =============================== MMA issuer (a pair: the leader CTA only) ===============================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TILE_M : TILE_M, (uint32_t)block_n);
       int s = 0;
       uint32_t phase = 0;
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait_relaxed(&full_bar[s], phase);
-        if (CFENCE) fence_proxy_async_smem();   // producers' st.shared (acquired above) -> visible to the UMMA reads
+        if (PAIR) {
+          mbar_wait_relaxed_cluster(&full_bar[s], phase);
+          fence_proxy_async_all();             // st.shared of BOTH CTAs' producers (acquired above) -> visible to the UMMA reads
+        } else {
+          mbar_wait_relaxed(&full_bar[s], phase);
+          fence_proxy_async_smem();            // producers' st.shared (acquired above) -> visible to the UMMA reads
+        }
         tcgen05_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * L.stage_bytes);
         const uint64_t bdesc = umma_desc_sw128(a_addr + M_TILES * A_TILE_BYTES);
@@ -448,30 +508,29 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
         for (int mt = 0; mt < M_TILES; ++mt) {
           const uint64_t adesc = umma_desc_sw128(a_addr + mt * A_TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_bf16(tmem_base + (uint32_t)(mt * block_n), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+            if (PAIR) umma_bf16_pair(tmem_base + (uint32_t)(mt * block_n), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+            else umma_bf16(tmem_base + (uint32_t)(mt * block_n), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+          }
         }
-        umma_commit(&empty_bar[s]);          // stage reusable once these MMAs have read it
+        // stage reusable (in both CTAs of a pair) once these MMAs have read it
+        if (PAIR) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
         if (++s == stages) { s = 0; phase ^= 1u; }
       }
-      umma_commit(accum_bar);                // accumulators complete
+      if (PAIR) umma_commit_pair(accum_bar); else umma_commit(accum_bar);     // accumulators complete
     }
     __syncwarp();
   }
 
   // ---- teardown ----
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == PW + 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)a.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
-}
-
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
 }
 
 int pick_block_n(int out_c) {
@@ -482,34 +541,99 @@ int pick_block_n(int out_c) {
   return 0;
 }
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
-      (void)cudaGetLastError();
-      n = 148;
-    }
+SmemAttrCache g_smem_attr[16];         // one per instantiation below
+
+template <int M_TILES, int PW, int D, bool PAIR, bool PLAIN>
+int launch_t(const TcArgs& args, const CUtensorMap& tmap, dim3 grid, int smem_bytes, cudaStream_t stream) {
+  constexpr int slot = ((M_TILES - 1) * 2 + (PW == 16 ? 1 : 0)) * 4 + (PAIR ? 2 : 0) + (PLAIN ? 1 : 0);
+  auto kernel = dcn_tc_kernel<M_TILES, PW, D, PAIR, PLAIN>;
+  const int rc = ensure_dynamic_smem(kernel, smem_bytes, g_smem_attr[slot]);
+  if (rc != STM_OK) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(PW * 32 + 64);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.numAttrs = 0;
+  if (PAIR) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;      // the two CTAs of a pair: consecutive blockIdx.x, same TPC
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
   }
-  return n;
+  STM_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, args, tmap));
+  count_launch();
+  return STM_OK;
 }
 
-template <int M_TILES, int PW, int D, bool CFENCE>
-int launch_t(const TcArgs& args, const CUtensorMap& tmap, dim3 grid, int smem_bytes, cudaStream_t stream) {
-  static int configured = 0;
-  if (configured < smem_bytes) {
-    STM_CUDA_OK(cudaFuncSetAttribute(dcn_tc_kernel<M_TILES, PW, D, CFENCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = smem_bytes;
-  }
-  dcn_tc_kernel<M_TILES, PW, D, CFENCE><<<grid, PW * 32 + 64, smem_bytes, stream>>>(args, tmap);
-  count_launch();
-  STM_CUDA_OK(cudaGetLastError());
+// Everything the host decides about a launch: CTA shape, pairing, pipeline depth, grid.  A pure function of the
+// call's arguments and the device's SM count (no environment variables, no mutable state), shared by the
+// launcher and by stm_deform_conv2d_variant().
+struct TcPlan {
+  int block_n, n_tiles, m_tiles, pw, stages, smem_bytes, tmem_cols, blocks, grid_x;
+  bool two_ctas, pair, plain;
+};
+
+int make_plan(const StmDcnConv* conv, const DcnParams& p, TcPlan* out) {
+  TcPlan pl;
+  pl.block_n = pick_block_n(p.out_c);
+  pl.plain = (p.flags & STM_DCN_ZERO_OFFSET) != 0;
+  int64_t rows = 0;
+  for (int i = 0; i < p.n_probs; ++i) rows += p.prob[i].m_total;
+  pl.n_tiles = p.out_c / pl.block_n;
+  // two accumulators (256 rows) per CTA halve the weight traffic per row (B200: 0.205 -> 0.150 ms on the 24x40
+  // backbone layers); fall back to 128-row CTAs only when 256-row CTAs could not even half-fill the GPU
+  const int64_t ctas256 = ((rows + 255) / 256) * pl.n_tiles;
+  pl.m_tiles = (ctas256 >= device_sm_count() / 2 && 2 * pl.block_n <= 512) ? 2 : 1;
+  // N <= 128 (the C = 128 backbone stage): the MMA is cheap, the gather and the per-CTA prologue / epilogue
+  // dominate.  Two 128-row CTAs with 8 producer warps each share an SM (registers, 128 TMEM columns and
+  // < 113 KB shared memory each), so one CTA's prologue / epilogue hides behind the other's main loop
+  // (B200: 0.358 -> 0.323 ms on the 48x80 C=128 layers).  With N = 256 the doubled weight traffic costs more.
+  pl.two_ctas = pl.block_n <= 128 && pl.block_n >= 64 && !pl.plain;
+  if (pl.two_ctas) pl.m_tiles = 1;
+  // explicit, stateless overrides (tests force every CTA shape through the same entry point)
+  if ((conv->flags & STM_DCN_HINT_ROWS128) != 0) { pl.m_tiles = 1; pl.two_ctas = false; }
+  if ((conv->flags & STM_DCN_HINT_ROWS256) != 0 && 2 * pl.block_n <= 512) { pl.m_tiles = 2; pl.two_ctas = false; }
+  pl.pw = pl.two_ctas ? 8 : 16;
+  // CTA pairs (tcgen05 cta_group::2): each CTA fetches and keeps only half of the N tile's weights.  Pays when the
+  // B operand is a large share of the shared-memory traffic (N >= 128) and the launch fills the GPU with pairs.
+  pl.pair = !pl.two_ctas && pl.block_n >= 128 && pl.block_n % 32 == 0 && (conv->flags & STM_DCN_HINT_NO_PAIR) == 0;
+  const int rows_per_cta = TILE_M * pl.m_tiles;
+  pl.blocks = 0;
+  for (int i = 0; i < p.n_probs; ++i) pl.blocks += (p.prob[i].m_total + rows_per_cta - 1) / rows_per_cta;
+  if (pl.pair && pl.blocks * pl.n_tiles < device_sm_count()) pl.pair = false;      // small launch: keep every tile on its own SM
+  pl.grid_x = pl.pair ? (pl.blocks + 1) & ~1 : pl.blocks;                           // a pair's odd filler CTA owns no rows
+  int cols = 32;
+  while (cols < pl.m_tiles * pl.block_n) cols <<= 1;
+  pl.tmem_cols = cols;
+  // pipeline depth: as many stages as fit while leaving L1 some room for the gather's corner reuse
+  int budget = pl.m_tiles == 2 ? 172 * 1024 : (pl.two_ctas ? 110 * 1024 : 132 * 1024);
+  if ((conv->flags & STM_DCN_HINT_DEEP_PIPE) != 0) budget = 200 * 1024;
+  auto total = [&](int st) {
+    return pl.m_tiles == 2 ? SmemLayout<2>(pl.block_n, st, pl.pair).total : SmemLayout<1>(pl.block_n, st, pl.pair).total;
+  };
+  pl.stages = MAX_STAGES;
+  for (; pl.stages > 2; --pl.stages)
+    if (total(pl.stages) <= budget) break;
+  pl.smem_bytes = total(pl.stages);
+  if (pl.smem_bytes > SMEM_LIMIT) { set_error("tcgen05 DCN: shared memory %d B over the limit", pl.smem_bytes); return STM_ERR_UNSUPPORTED; }
+  *out = pl;
   return STM_OK;
 }
 
 }  // namespace
 
 bool dcn_tc_supported(const StmDcnConv* c, const StmDcnProblem* pr, int n, const char** why) {
+  if (!dcn_tc_shape_supported(c, pr, n, why)) return false;
+  if (get_tensormap_encoder() == nullptr) { *why = "cuTensorMapEncodeTiled unavailable"; return false; }
+  return true;
+}
+
+// everything but the driver: also answers on a machine without a GPU (launch-plan queries)
+bool dcn_tc_shape_supported(const StmDcnConv* c, const StmDcnProblem* pr, int n, const char** why) {
   *why = "";
   if (c->dtype != STM_BF16) { *why = "dtype is not bf16"; return false; }
   if (c->groups != 1) { *why = "groups != 1"; return false; }
@@ -526,36 +650,30 @@ bool dcn_tc_supported(const StmDcnConv* c, const StmDcnProblem* pr, int n, const
       return false;
     }
   }
-  if (get_tensormap_encoder() == nullptr) { *why = "cuTensorMapEncodeTiled unavailable"; return false; }
   return true;
 }
 
 size_t dcn_tc_workspace(const StmDcnConv*, const StmDcnProblem*, int) { return 0; }
 
+int dcn_tc_variant(const StmDcnConv* conv, const DcnParams& p, char* buf, size_t len) {
+  TcPlan pl;
+  const int rc = make_plan(conv, p, &pl);
+  if (rc != STM_OK) return rc;
+  snprintf(buf, len, "tcgen05 rows=%d n=%d pair=%d plain=%d producer_warps=%d stages=%d ctas_per_sm=%d grid=%dx%d", TILE_M * pl.m_tiles,
+           pl.block_n, pl.pair ? 1 : 0, pl.plain ? 1 : 0, pl.pw, pl.stages, pl.two_ctas ? 2 : 1, pl.grid_x, pl.n_tiles);
+  return STM_OK;
+}
+
 int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, cudaStream_t stream) {
   TcArgs args;
   args.p = p_in;
   DcnParams& p = args.p;
-  if (conv->offset_dtype == STM_BF16) p.flags |= 0x100;
-  const int block_n = pick_block_n(p.out_c);
-  int64_t rows = 0;
-  for (int i = 0; i < p.n_probs; ++i) rows += p.prob[i].m_total;
-  const int n_tiles = p.out_c / block_n;
-  // two accumulators (256 rows) per CTA halve the weight traffic per row (B200: 0.205 -> 0.150 ms on the 24x40
-  // backbone layers); fall back to 128-row CTAs only when 256-row CTAs could not even half-fill the GPU
-  const int64_t ctas256 = ((rows + 255) / 256) * n_tiles;
-  int m_tiles = (ctas256 >= sm_count() / 2 && 2 * block_n <= 512) ? 2 : 1;
-  // N <= 128 (the C = 128 backbone stage): the MMA is cheap, the gather and the per-CTA prologue / epilogue
-  // dominate.  Two 128-row CTAs with 8 producer warps each share an SM (registers, 128 TMEM columns and
-  // < 113 KB shared memory each), so one CTA's prologue / epilogue hides behind the other's main loop
-  // (B200: 0.358 -> 0.323 ms on the 48x80 C=128 layers).  With N = 256 the doubled weight traffic costs more.
-  bool two_ctas = block_n <= 128;
-  if (two_ctas) m_tiles = 1;
-  if (const char* e = getenv("STM_DCN_MTILES")) {           // tuning knob (profiling runs)
-    const int v = atoi(e);
-    if ((v == 1 || v == 2) && v * block_n <= 512) { m_tiles = v; two_ctas = false; }
-  }
-  const int rows_per_cta = TILE_M * m_tiles;
+  p.flags &= 0xffff;
+  if (conv->offset_dtype == STM_BF16) p.flags |= FLAG_OFFSETS_BF16;
+  TcPlan pl;
+  const int prc = make_plan(conv, p, &pl);
+  if (prc != STM_OK) return prc;
+  const int rows_per_cta = TILE_M * pl.m_tiles;
   int blocks = 0;
   for (int i = 0; i < p.n_probs; ++i) {
     p.prob[i].tile_begin = blocks;
@@ -563,34 +681,16 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   }
   p.total_m_tiles = blocks;
   if (blocks == 0) return STM_OK;
-  args.block_n = block_n;
-  int cols = 32;
-  while (cols < m_tiles * block_n) cols <<= 1;
-  args.tmem_cols = cols;
+  args.block_n = pl.block_n;
+  args.tmem_cols = pl.tmem_cols;
   args.pad_ = 0;
-  // pipeline depth: as many stages as fit while leaving L1 some room for the gather's corner reuse
-  int stages = MAX_STAGES, smem_bytes = 0;
-  int budget = m_tiles == 2 ? 172 * 1024 : (two_ctas ? 110 * 1024 : 132 * 1024);
-  if (const char* e = getenv("STM_DCN_SMEM_KB")) {          // tuning knob (profiling runs)
-    const int v = atoi(e);
-    if (v >= 64 && v <= 227) budget = v * 1024;
-  }
-  for (; stages >= 2; --stages) {
-    smem_bytes = m_tiles == 2 ? SmemLayout<2>(block_n, stages).total : SmemLayout<1>(block_n, stages).total;
-    if (smem_bytes <= budget) break;
-  }
-  if (stages < 2) {
-    stages = 2;
-    smem_bytes = m_tiles == 2 ? SmemLayout<2>(block_n, 2).total : SmemLayout<1>(block_n, 2).total;
-  }
-  if (smem_bytes > SMEM_LIMIT) { set_error("tcgen05 DCN: shared memory %d B over the limit", smem_bytes); return STM_ERR_UNSUPPORTED; }
-  args.stages = stages;
+  args.stages = pl.stages;
 
   CUtensorMap tmap;
   const cuuint64_t ktot = (cuuint64_t)p.kh * p.kw * p.in_c;
   const cuuint64_t dims[2] = {ktot, (cuuint64_t)p.out_c};
   const cuuint64_t strides[1] = {ktot * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n};
+  const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(pl.pair ? pl.block_n / 2 : pl.block_n)};
   const cuuint32_t estr[2] = {1, 1};
   PFN_stm_encodeTiled enc = get_tensormap_encoder();
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled unavailable"); return STM_ERR_CUDA; }
@@ -599,26 +699,18 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return STM_ERR_CUDA; }
 
-  const dim3 grid((unsigned)blocks, (unsigned)n_tiles);
-  // tuning knobs (profiling runs): producer warps and where the generic->async proxy fence is executed
-  const int pw = env_int("STM_DCN_PW", two_ctas ? 8 : 16);
-  const int depth = env_int("STM_DCN_DEPTH", 2);
-  const bool cfence = env_int("STM_DCN_CFENCE", 1) != 0;
-#define STM_LAUNCH(MT, PW_, D_) \
-  return cfence ? launch_t<MT, PW_, D_, true>(args, tmap, grid, smem_bytes, stream) : launch_t<MT, PW_, D_, false>(args, tmap, grid, smem_bytes, stream)
-  if (m_tiles == 2) {
-    if (pw == 8) {                // 8 gather tasks per thread per K block
-      if (depth >= 4) { STM_LAUNCH(2, 8, 4); }
-      STM_LAUNCH(2, 8, 2);
-    }
-    STM_LAUNCH(2, 16, 2);
+  const dim3 grid((unsigned)pl.grid_x, (unsigned)pl.n_tiles);
+#define STM_GO(MT, PW_, D_, PAIR_, PLAIN_) return launch_t<MT, PW_, D_, PAIR_, PLAIN_>(args, tmap, grid, pl.smem_bytes, stream)
+  if (pl.plain) {                      // regular convolution: every task of the next K block in flight (4 registers each)
+    if (pl.m_tiles == 2) { if (pl.pair) STM_GO(2, 16, 4, true, true); STM_GO(2, 16, 4, false, true); }
+    if (pl.pair) STM_GO(1, 16, 2, true, true);
+    STM_GO(1, 16, 2, false, true);
   }
-  if (pw == 8) {                  // 4 tasks
-    if (depth >= 4) { STM_LAUNCH(1, 8, 4); }
-    STM_LAUNCH(1, 8, 2);
-  }
-  STM_LAUNCH(1, 16, 2);           // 2 tasks
-#undef STM_LAUNCH
+  if (pl.m_tiles == 2) { if (pl.pair) STM_GO(2, 16, 2, true, false); STM_GO(2, 16, 2, false, false); }
+  if (pl.pw == 8) STM_GO(1, 8, 2, false, false);            // 4 gather tasks per thread per K block, two CTAs per SM
+  if (pl.pair) STM_GO(1, 16, 2, true, false);
+  STM_GO(1, 16, 2, false, false);                           // 2 tasks
+#undef STM_GO
 }
 
 }  // namespace stm

@@ -51,6 +51,7 @@ class FeatureAlign(nn.Module):
 
     def calibrate_levels(self, xs: Sequence[torch.Tensor], shapes: Sequence[torch.Tensor]) -> List[torch.Tensor]:
         """relu(conv_adaption(x, offset)) for every level, one launch."""
+        ops._no_grad_inputs(self.conv_adaption.weight, *xs)
         offs = [self.offsets(s) for s in shapes]
         spec = self.conv_adaption.spec()
         wp = self.conv_adaption._cache.weight(self.conv_adaption.weight, spec, xs[0].dtype)

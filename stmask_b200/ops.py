@@ -136,35 +136,61 @@ def pack_weight(weight: torch.Tensor, spec: ConvSpec, dtype: torch.dtype) -> tor
 
 
 class PackedWeightCache:
-    """Packed weights (and fp32 biases) keyed on the parameter's storage + version counter, so a
-    module re-packs only after its weight was modified (optimizer step, load_state_dict)."""
+    """Packed weights (and fp32 biases) of a module, re-packed only after the source tensor was modified.
+
+    An entry remembers the source tensor by WEAK REFERENCE together with its version counter and storage
+    address: a hit needs the very same tensor object (an address recycled by the caching allocator after the
+    original was freed can never alias), the same `_version` (in-place ops, optimizer steps, `load_state_dict`)
+    and the same `data_ptr()` / dtype (`module.to(...)`, `param.data = ...`).  The one thing this cannot see is
+    an in-place write THROUGH `.data` (`w.data.copy_(...)`, EMA swaps): autograd hides those from the version
+    counter by design — call `invalidate()` (or `module._cache.invalidate()`) after such a write."""
 
     def __init__(self, max_entries: int = 256):
         self._w = {}
         self._b = {}
         self._max = max_entries
 
+    def invalidate(self) -> None:
+        self._w.clear()
+        self._b.clear()
+
+    @staticmethod
+    def _alive(entry, t: torch.Tensor) -> bool:
+        return entry is not None and entry[0]() is t and entry[1] == (t._version, t.data_ptr(), t.dtype)
+
     def weight(self, weight: torch.Tensor, spec: ConvSpec, dtype: torch.dtype) -> torch.Tensor:
-        key = (weight.data_ptr(), weight._version, dtype, weight.device, tuple(weight.shape))
+        import weakref
+        key = (id(weight), dtype)
         hit = self._w.get(key)
-        if hit is None:
+        if not self._alive(hit, weight):
             if len(self._w) >= self._max:
                 self._w.clear()
-            hit = pack_weight(weight, spec, dtype)
+            hit = (weakref.ref(weight), (weight._version, weight.data_ptr(), weight.dtype), pack_weight(weight, spec, dtype))
             self._w[key] = hit
-        return hit
+        return hit[2]
 
     def bias(self, bias: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         if bias is None:
             return None
-        key = (bias.data_ptr(), bias._version, bias.device, bias.dtype)
+        import weakref
+        key = id(bias)
         hit = self._b.get(key)
-        if hit is None:
+        if not self._alive(hit, bias):
             if len(self._b) >= self._max:
                 self._b.clear()
-            hit = bias.detach().float().contiguous()
+            hit = (weakref.ref(bias), (bias._version, bias.data_ptr(), bias.dtype), bias.detach().float().contiguous())
             self._b[key] = hit
-        return hit
+        return hit[2]
+
+
+def _no_grad_inputs(*tensors: Optional[torch.Tensor]) -> None:
+    """The library is forward-only (the north star's scope): refuse, loudly, to produce outputs without a
+    grad_fn for inputs that require grad instead of silently cutting the autograd graph."""
+    if torch.is_grad_enabled():
+        for t in tensors:
+            if t is not None and t.requires_grad:
+                raise RuntimeError("stmask_b200 operators are forward-only (no autograd): call them under torch.no_grad() "
+                                   "or detach the inputs; an input or weight requires grad")
 
 
 def _check_offset(t: Optional[torch.Tensor], ch: int, b: int, ho: int, wo: int, what: str) -> None:
@@ -179,15 +205,19 @@ def deform_conv2d_multi(xs: Sequence[torch.Tensor], offsets: Sequence[Optional[t
                         masks: Optional[Sequence[Optional[torch.Tensor]]], w_packed: torch.Tensor,
                         bias_f32: Optional[torch.Tensor], spec: ConvSpec, *, relu: bool = False,
                         mask_sigmoid: bool = False, backend: str = "auto",
-                        outs: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+                        outs: Optional[Sequence[torch.Tensor]] = None, hint: int = 0,
+                        out_f32: bool = False) -> List[torch.Tensor]:
     """One launch over several feature maps that share one weight (e.g. the FPN levels of the
     shared prediction head, reference STMask.py:91-92 / prediction_head_FC.py:166-167).
 
     offsets[i] is None for every i  =>  plain convolution through the same kernel.
+    out_f32: the outputs are float32 whatever the activations' dtype (the fp32 accumulators are stored as they
+    are) — what the offset / mask-logit predictor of a DCN wants: sampling positions must not be rounded to bf16.
     """
     n = len(xs)
     if n == 0:
         return []
+    _no_grad_inputs(*xs, *[o for o in offsets if o is not None], *([m for m in masks if m is not None] if masks else []))
     if n > L.DCN_MAX_PROBLEMS:
         raise ValueError(f"at most {L.DCN_MAX_PROBLEMS} feature maps per launch, got {n}")
     if len(offsets) != n or (masks is not None and len(masks) != n):
@@ -244,10 +274,12 @@ def deform_conv2d_multi(xs: Sequence[torch.Tensor], offsets: Sequence[Optional[t
                 msk = msk.to(first.dtype)
         if outs is not None:
             y = outs[i]
-            if tuple(y.shape) != (b, spec.out_c, ho, wo) or y.dtype != x.dtype or not (spec.out_c == 1 or y.stride(1) == 1):
+            if tuple(y.shape) != (b, spec.out_c, ho, wo) or y.dtype != (torch.float32 if out_f32 else x.dtype) or \
+                    not (spec.out_c == 1 or y.stride(1) == 1):
                 raise ValueError("preallocated output must be a channels-last tensor of the right shape/dtype")
         else:
-            y = torch.empty((b, spec.out_c, ho, wo), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
+            y = torch.empty((b, spec.out_c, ho, wo), dtype=torch.float32 if out_f32 else x.dtype, device=dev,
+                            memory_format=torch.channels_last)
         keep += [xn, off, msk, y]
         ys.append(y)
         p = probs[i]
@@ -263,6 +295,9 @@ def deform_conv2d_multi(xs: Sequence[torch.Tensor], offsets: Sequence[Optional[t
         p.y = y.data_ptr()
         p.y_stride_n, p.y_stride_h, p.y_stride_w = y.stride(0), y.stride(2), y.stride(3)
     flags = (L.DCN_RELU if relu else 0) | (L.DCN_MASK_SIGMOID if mask_sigmoid else 0) | (L.DCN_ZERO_OFFSET if zero_offset else 0)
+    flags |= int(hint) & (L.DCN_HINT_ROWS128 | L.DCN_HINT_ROWS256 | L.DCN_HINT_NO_PAIR | L.DCN_HINT_DEEP_PIPE)
+    if out_f32:
+        flags |= L.DCN_OUT_F32
     conv = spec.c_struct(xdt, odt, flags, _BACKENDS[backend])
     if bias_f32 is not None:
         _require_cuda(bias_f32, "bias")
@@ -298,21 +333,94 @@ def deform_conv2d_backend(x_shape: Sequence[int], spec: ConvSpec, dtype: torch.d
     return L.BACKEND_NAMES[rc]
 
 
+def deform_conv2d_variant(x_shapes: Sequence[Sequence[int]], spec: ConvSpec, dtype: torch.dtype, backend: str = "auto",
+                          hint: int = 0, device=None, zero_offset: bool = False) -> str:
+    """The kernel instantiation a launch over feature maps of these shapes would run on `device`
+    (e.g. 'tcgen05 rows=256 n=256 producer_warps=16 stages=2 pair=1 ...') — shape-only query."""
+    n = len(x_shapes)
+    prob = (L.StmDcnProblem * n)()
+    for p, (b, _, h, w) in zip(prob, x_shapes):
+        ho, wo = spec.out_hw(h, w)
+        p.batch, p.in_h, p.in_w, p.out_h, p.out_w = b, h, w, ho, wo
+        p.x = p.y = p.offset = 256
+        p.x_stride_w, p.x_stride_h, p.x_stride_n = spec.in_c, spec.in_c * w, spec.in_c * w * h
+        p.y_stride_w, p.y_stride_h, p.y_stride_n = spec.out_c, spec.out_c * wo, spec.out_c * wo * ho
+    dt = L.STM_F32 if dtype == torch.float32 else L.STM_BF16
+    conv = spec.c_struct(dt, L.STM_F32, int(hint) | (L.DCN_ZERO_OFFSET if zero_offset else 0), _BACKENDS[backend])
+    buf = C.create_string_buffer(256)
+    import contextlib
+    ctx = torch.cuda.device(device if device is not None else torch.cuda.current_device()) if torch.cuda.is_available() \
+        else contextlib.nullcontext()      # without a GPU the plan assumes a B200's 148 SMs
+    with ctx:
+        L.check(L.lib().stm_deform_conv2d_variant(C.byref(conv), prob, n, buf, 256), "stm_deform_conv2d_variant")
+    return buf.value.decode()
+
+
+_functional_cache = PackedWeightCache(max_entries=64)
+
+
 def deform_conv2d(x: torch.Tensor, offset: Optional[torch.Tensor], weight: torch.Tensor,
                   bias: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, stride: IntPair = 1,
                   padding: IntPair = 0, dilation: IntPair = 1, groups: int = 1, deform_groups: int = 1, *,
                   relu: bool = False, mask_sigmoid: bool = False, backend: str = "auto",
-                  cache: Optional[PackedWeightCache] = None) -> torch.Tensor:
-    """DCNv1 (mask None) / DCNv2 forward with an OIHW weight (packed on the fly or via `cache`)."""
+                  cache: Optional[PackedWeightCache] = None, hint: int = 0) -> torch.Tensor:
+    """DCNv1 (mask None) / DCNv2 forward with an OIHW weight.  The packed copy of the weight is cached (the
+    functional drop-ins `dcn_v2_conv`, `mmcv.ops.deform_conv2d`, `modulated_deform_conv2d` therefore pack once
+    per weight tensor, not once per call); entries are tied to the weight OBJECT by weak reference, so they
+    can neither alias a new tensor at a recycled address nor outlive the weight."""
     _require_cuda(x, "x")
     _require_cuda(weight, "weight")
+    _no_grad_inputs(weight, bias)
     spec = ConvSpec(x.shape[1] if x.dim() == 4 else -1, weight.shape[0], weight.shape[2:], stride, padding, dilation,
                     groups, deform_groups)
-    cache = cache or PackedWeightCache()
+    cache = cache if cache is not None else _functional_cache
     wp = cache.weight(weight, spec, x.dtype)
     bf = cache.bias(bias)
     return deform_conv2d_multi([x], [offset], [mask] if mask is not None else None, wp, bf, spec, relu=relu,
-                               mask_sigmoid=mask_sigmoid, backend=backend)[0]
+                               mask_sigmoid=mask_sigmoid, backend=backend, hint=hint)[0]
+
+
+class PlainConv:
+    """A regular convolution (+ bias, optional ReLU) run through the deformable-conv kernels in their zero-offset
+    mode: tcgen05 implicit GEMM with copy-only producers for bf16 NHWC activations whose channel count is a multiple
+    of 64, the CUDA-core kernel otherwise.  Used for the offset / mask-logit predictor of `DCN` (fp32 output) and for
+    the TemporalNet convs.  Holds the packed weight (output channels zero-padded to a multiple of 16) and the fp32
+    bias of ONE nn.Conv2d-like parameter pair, re-packed when the parameters change."""
+
+    def __init__(self):
+        self._key = None
+        self._packed = None
+
+    def _refresh(self, weight: torch.Tensor, bias: Optional[torch.Tensor], dtype: torch.dtype, in_pad: Optional[Tuple[int, int]]):
+        key = (id(weight), weight._version, weight.data_ptr(), weight.dtype, dtype, in_pad,
+               None if bias is None else (id(bias), bias._version, bias.data_ptr()))
+        if key != self._key:
+            co = weight.shape[0]
+            cp = (co + 15) // 16 * 16
+            w = weight.detach()
+            if in_pad is not None:            # insert zero input channels at [at, at + n) (padded concat layout)
+                at, n = in_pad
+                w = torch.cat([w[:, :at], w.new_zeros((co, n) + tuple(w.shape[2:])), w[:, at:]], dim=1)
+            if cp != co:
+                w = torch.cat([w, w.new_zeros((cp - co,) + tuple(w.shape[1:]))], dim=0)
+            spec = ConvSpec(w.shape[1], cp, w.shape[2:])
+            b = None
+            if bias is not None:
+                b = torch.zeros(cp, dtype=torch.float32, device=weight.device)
+                b[:co] = bias.detach().float()
+            self._packed = (pack_weight(w.contiguous(), spec, dtype), b, cp)
+            self._key = key
+        return self._packed
+
+    def __call__(self, xs: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor], stride: IntPair = 1,
+                 padding: IntPair = 0, dilation: IntPair = 1, *, relu: bool = False, out_f32: bool = False,
+                 in_pad: Optional[Tuple[int, int]] = None, backend: str = "auto", hint: int = 0) -> List[torch.Tensor]:
+        """-> list of [B, Cout_padded, Ho, Wo] channels-last tensors (slice [:, :Cout] is the convolution)."""
+        _no_grad_inputs(weight, bias, *xs)
+        wp, b, cp = self._refresh(weight, bias, xs[0].dtype, in_pad)
+        spec = ConvSpec(xs[0].shape[1], cp, weight.shape[2:], stride, padding, dilation)
+        return deform_conv2d_multi(list(xs), [None] * len(xs), None, wp, b, spec, relu=relu, backend=backend, hint=hint,
+                                   out_f32=out_f32)
 
 
 def fcb_ali_offsets(shape: torch.Tensor, kernel_size: IntPair, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
@@ -437,6 +545,31 @@ def correlation(x1: torch.Tensor, x2: torch.Tensor, patch_size: int = 11, dilati
     return out
 
 
+_checked_indices = {}
+
+
+def _check_pair_indices(ref_index: torch.Tensor, next_index: torch.Tensor, frames: int, halo_frames: int) -> None:
+    """Range-check the pair index arrays ONCE per (tensor, version): 0 <= next < F and 0 <= ref < F + halo frames
+    (a ref >= F addresses the halo, so a halo must be present).  The check reads the indices back to the host,
+    which is why the verdict is remembered for the (persistent, cached) index tensors sharding.py hands out."""
+    if ref_index.numel() == 0:
+        return
+    import weakref
+    key = (id(ref_index), id(next_index))
+    hit = _checked_indices.get(key)
+    sig = (ref_index._version, next_index._version, frames, halo_frames)
+    if hit is not None and hit[0]() is ref_index and hit[1]() is next_index and hit[2] == sig:
+        return
+    lo = int(torch.minimum(ref_index.min(), next_index.min()))
+    rmax, nmax = int(ref_index.max()), int(next_index.max())
+    if lo < 0 or nmax >= frames or rmax >= frames + halo_frames:
+        raise ValueError(f"pair indices out of range: ref in [{lo}, {rmax}], next max {nmax}, {frames} frames + {halo_frames} "
+                         f"halo frames (a ref index >= {frames} needs a halo tensor)")
+    if len(_checked_indices) > 64:
+        _checked_indices.clear()
+    _checked_indices[key] = (weakref.ref(ref_index), weakref.ref(next_index), sig)
+
+
 def correlation_pairs(x: torch.Tensor, ref_index: torch.Tensor, next_index: torch.Tensor, patch_size: int = 11,
                       dilation_patch: int = 1, *, scale: float = 1.0, leaky_slope: Optional[float] = None, relu: bool = False,
                       feats: Optional[torch.Tensor] = None, halo: Optional[torch.Tensor] = None,
@@ -460,6 +593,8 @@ def correlation_pairs(x: torch.Tensor, ref_index: torch.Tensor, next_index: torc
         raise ValueError("patch_size must be odd and positive, dilation_patch >= 1")
     f, c, h, w = x.shape
     n = ref_index.numel()
+    n_halo = int(halo.shape[0]) if halo is not None else 0
+    _check_pair_indices(ref_index, next_index, f, n_halo)
     a = to_nhwc(x)
     flags = 0
     if leaky_slope is not None:
@@ -584,15 +719,12 @@ def roi_align(input: torch.Tensor, rois: torch.Tensor, output_size=7, spatial_sc
 # --------------------------------------------------------------------------------------------
 # torch.library registration (CUDA key only, fake impl for shape inference, no CPU key)
 # --------------------------------------------------------------------------------------------
-_op_cache = PackedWeightCache()
-
-
 @torch.library.custom_op("stmask_b200::deform_conv2d", mutates_args=(), device_types="cuda")
 def _deform_conv2d_op(x: torch.Tensor, offset: torch.Tensor, mask: Optional[torch.Tensor], weight: torch.Tensor,
                       bias: Optional[torch.Tensor], stride: List[int], padding: List[int], dilation: List[int],
                       groups: int, deform_groups: int, relu: bool, mask_sigmoid: bool) -> torch.Tensor:
     return deform_conv2d(x, offset, weight, bias, mask, stride, padding, dilation, groups, deform_groups, relu=relu,
-                         mask_sigmoid=mask_sigmoid, cache=_op_cache)
+                         mask_sigmoid=mask_sigmoid)
 
 
 @_deform_conv2d_op.register_fake

@@ -34,7 +34,8 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name)
     lib.stm_version.restype = ctypes.c_int
-    assert lib.stm_version() == 4
+    from stmask_b200 import _lib as _b
+    assert lib.stm_version() == _b.ABI_VERSION
     lib.stm_last_error.restype = ctypes.c_char_p
     assert lib.stm_last_error() == b""
 
@@ -150,3 +151,62 @@ def test_fake_impls_give_shapes_without_a_gpu():
         assert tuple(y.shape) == (2, 256, 24, 40)
         c = torch.ops.stmask_b200.correlation(x, x, 11, 1, 1.0 / 256, 0.1, False)
         assert tuple(c.shape) == (2, 121, 24, 40)
+
+
+def test_mmcv_shim_falls_through_to_a_real_mmcv(tmp_path):
+    """shims/ ahead on PYTHONPATH must not shadow the rest of mmcv: a 'real' mmcv further down the path keeps
+    serving imread / is_str / parallel / runner, only the hot-path names of mmcv.ops are replaced."""
+    real = tmp_path / "site" / "mmcv"
+    (real / "parallel").mkdir(parents=True)
+    (real / "ops").mkdir()
+    (real / "__init__.py").write_text("from .parallel import DataContainer\n__version__ = '1.1.2'\n"
+                                      "def imread(p):\n    return ('imread', p)\ndef is_str(x):\n    return isinstance(x, str)\n")
+    (real / "parallel" / "__init__.py").write_text("class DataContainer:\n    pass\ndef collate(b):\n    return b\n")
+    (real / "ops" / "__init__.py").write_text("raise ImportError('mmcv._ext is not built')\n")      # mmcv-full without its extension
+    code = ("import mmcv, mmcv.ops\n"
+            "from mmcv.ops import DeformConv2d, roi_align\n"
+            "from mmcv.parallel import DataContainer, collate\n"
+            "assert mmcv.imread('x') == ('imread', 'x') and mmcv.is_str('a') and mmcv.__version__ == '1.1.2'\n"
+            "assert DeformConv2d.__module__ == 'stmask_b200.compat.mmcv_ops' and mmcv.ops.__stmask_b200__\n"
+            "import dcn_v2, spatial_correlation_sampler\n"
+            "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "shims"), ROOT, str(tmp_path / "site")]))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+    # without any real mmcv: a namespace with mmcv.ops alone; and the PYTHONPATH-free form
+    code2 = ("import stmask_b200\nstmask_b200.install_shims()\n"
+             "from mmcv.ops import roi_align, ModulatedDeformConv2d\nfrom dcn_v2 import DCN\n"
+             "from spatial_correlation_sampler import spatial_correlation_sample, SpatialCorrelationSampler\nprint('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=ROOT), cwd=str(tmp_path))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_launch_plan_is_a_pure_function_of_the_call():
+    """stm_deform_conv2d_variant: which tcgen05 instantiation a call runs (no environment knobs; hints travel with the
+    call).  Without a GPU the SM count defaults to 148 (B200)."""
+    import torch
+    from stmask_b200 import _lib, ops
+    fpn = [(72, 256, h, w) for h, w in ((48, 80), (24, 40), (12, 20), (6, 10), (3, 5))]
+    fcb = ops.ConvSpec(256, 256, (3, 5), 1, (1, 2))
+    v = ops.deform_conv2d_variant(fpn, fcb, torch.bfloat16)
+    assert "tcgen05 rows=256 n=256 pair=1 plain=0" in v, v
+    assert "pair=0" in ops.deform_conv2d_variant(fpn, fcb, torch.bfloat16, hint=_lib.DCN_HINT_NO_PAIR)
+    assert "rows=128" in ops.deform_conv2d_variant(fpn, fcb, torch.bfloat16, hint=_lib.DCN_HINT_ROWS128)
+    assert ops.deform_conv2d_variant(fpn, fcb, torch.float32) == "simt"
+    small = ops.deform_conv2d_variant([(2, 256, 12, 20)], fcb, torch.bfloat16)
+    assert "rows=128" in small and "pair=0" in small, small          # 480 rows: 4 CTAs, nothing to pair
+    c128 = ops.deform_conv2d_variant([(72, 128, 48, 80)], ops.ConvSpec(128, 128, 3, 1, 1), torch.bfloat16)
+    assert "rows=128 n=128" in c128 and "ctas_per_sm=2" in c128, c128
+    pred = ops.deform_conv2d_variant([(72, 256, 24, 40)], ops.ConvSpec(256, 32, 3, 1, 1), torch.bfloat16, zero_offset=True)
+    assert "plain=1" in pred and "n=32" in pred, pred
+    for k in ("STM_DCN_MTILES", "STM_DCN_PW", "STM_CORR_TW"):          # no hidden global state behind the ABI
+        os.environ[k] = "1"
+    try:
+        assert ops.deform_conv2d_variant(fpn, fcb, torch.bfloat16) == v
+    finally:
+        for k in ("STM_DCN_MTILES", "STM_DCN_PW", "STM_CORR_TW"):
+            os.environ.pop(k)
+    src = "".join(open(os.path.join(ROOT, "stmask_b200", "csrc", f)).read() for f in os.listdir(os.path.join(ROOT, "stmask_b200", "csrc")))
+    import re as _re
+    stripped = _re.sub(r"#ifdef STM_DCN_EXPERIMENTS.*?#endif", "", src, flags=_re.S)
+    assert "getenv" not in stripped

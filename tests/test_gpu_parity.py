@@ -188,8 +188,25 @@ def test_dcn_multi_level_launch_matches_single(cuda_device):
 # ------------------------------------------------------------------------------------------
 # module-level parity with the reference's call sites (golden fixtures)
 # ------------------------------------------------------------------------------------------
+def _oracle_dcn_module(x, weight, bias, com_w, com_b, stride, dtype):
+    """The reference's DCN.forward chain on (rounded) numpy inputs: predictor conv -> chunk/cat -> sigmoid -> DCNv2."""
+    k = com_w.shape[2]
+    pad = (k - 1) // 2
+    B, _, H, W = x.shape
+    Ho, Wo = oracle.out_size(H, k, stride, pad, 1), oracle.out_size(W, k, stride, pad, 1)
+    zero = np.zeros((B, 2 * k * k, Ho, Wo), np.float32)
+    om = oracle.deform_conv2d(x, zero, com_w, com_b, None, stride=stride, padding=pad)      # zero offsets == regular conv
+    n_off = 2 * k * k
+    mask = 1.0 / (1.0 + np.exp(-om[:, n_off:].astype(np.float64)))
+    return oracle.deform_conv2d(x, om[:, :n_off], weight, bias, mask.astype(np.float32), stride=stride, padding=pad), om
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_backbone_dcn_module_vs_reference(cuda_device, dtype):
+    """The drop-in `DCN` (own fp32-output offset/mask predictor + modulated deformable conv) against the golden
+    from the reference's own Bottleneck DCN branch (backbone.py:20-26,45).  fp32: the golden itself, 1e-4.
+    bf16: inputs and parameters rounded to bf16 first, the oracle runs the same chain on the rounded values, 1e-2
+    (the predictor's accumulators stay fp32, so sampling positions are not rounded)."""
     from stmask_b200.backbone_dcn import make_bottleneck_dcn
     z = load_golden("backbone_dcn.npz")
     for name, stride in (("s1", 1), ("s2", 2)):
@@ -203,10 +220,43 @@ def test_backbone_dcn_module_vs_reference(cuda_device, dtype):
         x = dev(z[f"{name}.dcn_x"], dtype, cuda_device)
         with torch.no_grad():
             y = m(x)
-        # bf16: the offset predictor itself runs in bf16, which moves sampling positions; compare
-        # against the fp32 golden with the bf16 tolerance scaled by the offset sensitivity
-        tol = 1e-4 if dtype == torch.float32 else 3e-2
-        assert rel_err(y.float().cpu().numpy(), z[f"{name}.dcn_y"]) <= tol
+        if dtype == torch.float32:
+            assert rel_err(y.float().cpu().numpy(), z[f"{name}.dcn_y"]) <= 1e-4
+        want, _ = _oracle_dcn_module(q(z[f"{name}.dcn_x"], dtype), q(z[f"{name}.weight"], dtype), q(z[f"{name}.bias"], dtype),
+                                     q(z[f"{name}.com_w"], dtype), q(z[f"{name}.com_b"], dtype), stride, dtype)
+        assert rel_err(y.float().cpu().numpy(), want) <= TOL[dtype], (name, rel_err(y.float().cpu().numpy(), want))
+
+
+@pytest.mark.parametrize("case", [(256, 24, 40, 1, 20), (128, 48, 80, 2, 6), (512, 12, 20, 1, 8)],
+                         ids=lambda c: f"C{c[0]}_{c[1]}x{c[2]}_s{c[3]}_F{c[4]}")
+def test_backbone_dcn_module_tcgen05_vs_oracle(cuda_device, case):
+    """Same chain at backbone channel counts, bf16, so that BOTH kernels of the module are the tcgen05 ones (the
+    plain-conv predictor with fp32 output and the sampling kernel); non-zero predictor weights."""
+    from stmask_b200 import ops
+    from stmask_b200.compat.dcn_v2 import DCN
+    C, H, W, s, F = case
+    rng = np.random.default_rng(C + s)
+    x = q(rng.standard_normal((F, C, H, W)), torch.bfloat16)
+    w = q(rng.standard_normal((C, C, 3, 3)) / np.sqrt(9 * C), torch.bfloat16)
+    b = q(rng.standard_normal(C) * 0.1, torch.bfloat16)
+    cw = q(rng.standard_normal((27, C, 3, 3)) * 0.05 / 3, torch.bfloat16)
+    cb = q(rng.standard_normal(27) * 0.5, torch.bfloat16)
+    m = DCN(C, C, 3, s, 1).to(cuda_device)
+    with torch.no_grad():
+        m.weight.copy_(torch.from_numpy(w)); m.bias.copy_(torch.from_numpy(b))
+        m.conv_offset_mask.weight.copy_(torch.from_numpy(cw)); m.conv_offset_mask.bias.copy_(torch.from_numpy(cb))
+    m = m.to(torch.bfloat16)
+    xd = dev(x, torch.bfloat16, cuda_device, channels_last=True)
+    pred_spec = ops.ConvSpec(C, 32, 3, s, 1)
+    assert "plain=1" in ops.deform_conv2d_variant([tuple(xd.shape)], pred_spec, torch.bfloat16, zero_offset=True)
+    with torch.no_grad():
+        y = m(xd)
+        om = m._predictor([xd], m.conv_offset_mask.weight, m.conv_offset_mask.bias, s, 1, 1, out_f32=True)[0]
+    want, want_om = _oracle_dcn_module(x, w, b, cw, cb, s, torch.bfloat16)
+    assert om.dtype == torch.float32 and om.shape[1] == 32
+    assert rel_err(om[:, :27].cpu().numpy(), want_om) <= 1e-4          # fp32 accumulators stored as fp32
+    assert float(om[:, 27:].abs().max()) == 0.0
+    assert rel_err(y.float().cpu().numpy(), want) <= 1e-2
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -242,6 +292,7 @@ def test_feature_align_vs_reference(cuda_device, dtype, mode):
             assert rel_err(dcn.float().cpu().numpy(), want) <= 1e-2, k
 
 
+@torch.no_grad()
 def test_drop_in_modules_match_functional(cuda_device):
     from dcn_v2 import DCN, DCNv2, dcn_v2_conv
     from mmcv.ops import DeformConv2d, ModulatedDeformConv2d, ModulatedDeformConv2dPack, deform_conv2d, modulated_deform_conv2d
@@ -530,8 +581,70 @@ def test_forward_streamed_equals_resident_step(cuda_device):
     for _ in range(2):                                         # second pass reuses the staging buffers
         hp.forward_streamed(host_in, host_out, io, plan, 0)
     for k, v in want.items():
-        if k.startswith("dcn"):
-            # the offset/mask predictor is a cuDNN conv whose algorithm may change with the batch size of a chunk
-            assert rel_err(host_out[k].float().numpy(), v.float().cpu().numpy()) <= 2e-2, k
-        else:
-            assert torch.equal(host_out[k], v.cpu()), k
+        # every operator on the path (the DCN's offset/mask predictor included) is this library's own deterministic
+        # kernel: chunked and whole-batch runs agree bit for bit
+        assert torch.equal(host_out[k], v.cpu()), k
+
+
+# ------------------------------------------------------------------------------------------
+# host-side contracts: forward-only guard, packed-weight cache identity, pair-index validation
+# ------------------------------------------------------------------------------------------
+def test_forward_only_guard_raises_instead_of_cutting_the_graph(cuda_device):
+    from dcn_v2 import DCN
+    from mmcv.ops import DeformConv2d
+    x = torch.randn(1, 16, 6, 6, device=cuda_device)
+    off = torch.zeros(1, 18, 6, 6, device=cuda_device)
+    m = DeformConv2d(16, 16, 3, padding=1).to(cuda_device)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        m(x, off)                                        # weight requires grad and grad mode is on
+    with pytest.raises(RuntimeError, match="forward-only"):
+        DCN(16, 16, 3, 1, 1).to(cuda_device)(x)
+    with torch.no_grad():
+        assert m(x, off).shape == (1, 16, 6, 6)
+    assert _ops().deform_conv2d(x.requires_grad_(False), off, m.weight.detach(), padding=1).shape == (1, 16, 6, 6)
+
+
+def test_packed_weight_cache_cannot_alias_a_recycled_address(cuda_device):
+    """A freed weight's address is routinely handed to the next same-shape tensor by the caching allocator; the
+    functional entry points must not serve the old packed copy for it."""
+    ops = _ops()
+    torch.manual_seed(0)
+    x = torch.randn(1, 32, 8, 8, device=cuda_device)
+    off = torch.zeros(1, 18, 8, 8, device=cuda_device)
+    seen = set()
+    for i in range(6):
+        w = torch.randn(32, 32, 3, 3, device=cuda_device)          # _version 0 every time
+        seen.add(w.data_ptr())
+        got = ops.deform_conv2d(x, off, w, padding=1)
+        ref = torch.nn.functional.conv2d(x, w, padding=1)
+        assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) <= 1e-4, i
+        again = ops.deform_conv2d(x, off, w, padding=1)             # second call: served from the cache
+        assert torch.equal(got, again)
+        del w
+    assert len(seen) < 6                                            # the allocator did recycle an address
+    # `.data` writes are invisible to the version counter: documented, explicit invalidate()
+    w = torch.randn(32, 32, 3, 3, device=cuda_device)
+    cache = ops.PackedWeightCache()
+    a = ops.deform_conv2d(x, off, w, padding=1, cache=cache)
+    w.data.mul_(2.0)
+    cache.invalidate()
+    b = ops.deform_conv2d(x, off, w, padding=1, cache=cache)
+    assert rel_err(b.cpu().numpy(), 2 * a.cpu().numpy()) <= 1e-6
+
+
+def test_pair_indices_are_validated(cuda_device):
+    ops = _ops()
+    x = torch.randn(4, 64, 6, 10, device=cuda_device).bfloat16().contiguous(memory_format=torch.channels_last)
+    i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=cuda_device)
+    with pytest.raises(ValueError, match="out of range"):
+        ops.correlation_pairs(x, i32([0, 4]), i32([1, 2]), 11, 1)           # ref 4 >= 4 frames and no halo
+    with pytest.raises(ValueError, match="out of range"):
+        ops.correlation_pairs(x, i32([0, 1]), i32([1, 7]), 11, 1)
+    with pytest.raises(ValueError, match="out of range"):
+        ops.correlation_pairs(x, i32([-1, 1]), i32([1, 2]), 11, 1)
+    # misaligned base with pair indexing: an error, not a silent fall-back to the un-indexed CUDA-core kernel
+    from stmask_b200 import _lib
+    flat = torch.randn(4 * 64 * 6 * 10 + 8, device=cuda_device).bfloat16()
+    mis = flat[1:1 + 4 * 64 * 6 * 10].view(4, 6, 10, 64).permute(0, 3, 1, 2)     # 2-byte aligned NHWC view
+    with pytest.raises(_lib.StmError, match="aligned"):
+        ops.correlation_pairs(mis, i32([0, 1]), i32([1, 2]), 11, 1)
