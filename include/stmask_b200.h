@@ -84,7 +84,8 @@ enum {
   STM_DCN_HINT_NO_PAIR = 64, /* do not pair CTAs (tcgen05 cta_group::1 only)                         */
   STM_DCN_OUT_F32 = 128,     /* y is float32 [.., out_c] (strides in float elements) whatever conv->dtype:
                                 the offset / mask-logit predictor of a DCN keeps its fp32 accumulators   */
-  STM_DCN_HINT_DEEP_PIPE = 256 /* prefer more pipeline stages over L1 capacity                          */
+  STM_DCN_HINT_DEEP_PIPE = 256, /* prefer more pipeline stages over L1 capacity                         */
+  STM_DCN_HINT_TWO_CTAS = 512   /* two 128-row CTAs with 8 producer warps each per SM                   */
 };
 
 /* Parameters shared by every problem of one call (one weight tensor). */

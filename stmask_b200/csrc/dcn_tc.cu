@@ -106,9 +106,14 @@ __device__ __forceinline__ uint64_t add_wide(uint32_t lo, uint32_t hi, uint32_t 
 // TMEM lanes in each CTA) reads both halves.  Per CTA that halves the weight bytes fetched from L2 and the
 // shared-memory bytes the tensor core reads for the B operand (B is 2/3 of the operand traffic at N = 256) —
 // the shared-memory/L1 data pipe is what bounds this kernel (gather loads, A-tile stores and UMMA operand
-// reads all go through it).  Synchronisation: the producer warps and the weight TMA of BOTH CTAs arrive on the
-// LEADER's full barrier (remote mbarrier arrive / complete_tx), the leader's tcgen05.commit multicasts to the
-// empty barriers of both CTAs.
+// reads all go through it).  Synchronisation: every CTA's producer warps arrive on their OWN full barrier.  In
+// the leader that barrier also collects the weight TMA of BOTH CTAs (the peer's TMA completes its bytes on the
+// leader's barrier) and one arrival per K block from the peer's RELAY thread (the peer's otherwise idle MMA
+// warp): it waits for the peer's A tile, runs the generic->async proxy fence ON THE PEER SM (whose tensor core
+// reads that tile) and forwards one remote arrive.  Data never crosses CTAs through the generic proxy, only
+// that signal does, so all barrier operations keep CTA scope (cluster-scope release / acquire compile to
+// MEMBAR.ALL.GPU / CCTL.IVALL per K block — measured 40 % slower than no pairing at all).  The leader's
+// tcgen05.commit multicasts to the empty barriers of both CTAs.
 //
 // PLAIN: zero offsets (STM_DCN_ZERO_OFFSET): the sample is the pixel itself, so a gather task is ONE 16-byte
 // load and a store (no blend) and the metadata is one pointer per row.  This is the regular convolution that
@@ -125,7 +130,6 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   constexpr int NC = PLAIN ? 1 : 4;                     // corner loads per gather task
   static_assert(CPT == 1 || CPT == 2 || CPT == 4, "metadata split");
   static_assert(D >= 1 && D <= TPK && TPK % D == 0, "gather look-ahead must divide the tasks per K block");
-  static_assert(!PAIR || !(M_TILES == 1 && PW == 8), "CTA pairs run one CTA per SM");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const SmemLayout<M_TILES> L(a.block_n, a.stages, PAIR);
@@ -154,8 +158,9 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   if (warp == PW && lane == 0) {
     prefetch_tensormap(&tmap_w);
     for (int s = 0; s < stages; ++s) {
-      // producer warps (of both CTAs of a pair) + the (leader's) TMA thread's expect_tx arrive
-      mbar_init(&full_bar[s], PAIR ? 2 * PW + 1 : PW + 1);
+      // producer warps + the TMA thread's expect_tx arrive (+ the peer's relay thread in a pair's leader);
+      // a pair's non-leader: its producer warps only (its relay thread is the waiter)
+      mbar_init(&full_bar[s], !PAIR ? PW + 1 : (leader ? PW + 2 : PW));
       mbar_init(&empty_bar[s], 1);                   // tcgen05.commit
     }
     mbar_init(accum_bar, 1);
@@ -402,10 +407,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       }
       // this warp's part of the A tile of `stage` is complete
       __syncwarp();
-      if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(full_leader + (uint32_t)stage * 8u);
-        else mbar_arrive(&full_bar[stage]);
-      }
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
       if (++stage == stages) { stage = 0; phase ^= 1u; }
       it = nit; cc = ncc;
     }
@@ -494,13 +496,8 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       uint32_t phase = 0;
 #pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
-        if (PAIR) {
-          mbar_wait_relaxed_cluster(&full_bar[s], phase);
-          fence_proxy_async_all();             // st.shared of BOTH CTAs' producers (acquired above) -> visible to the UMMA reads
-        } else {
-          mbar_wait_relaxed(&full_bar[s], phase);
-          fence_proxy_async_smem();            // producers' st.shared (acquired above) -> visible to the UMMA reads
-        }
+        if (a.pad_ & 1) mbar_wait(&full_bar[s], phase); else mbar_wait_relaxed(&full_bar[s], phase);
+        fence_proxy_async_smem();              // this CTA's producers' st.shared (acquired above) -> visible to the UMMA reads
         tcgen05_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * L.stage_bytes);
         const uint64_t bdesc = umma_desc_sw128(a_addr + M_TILES * A_TILE_BYTES);
@@ -519,6 +516,17 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
         if (++s == stages) { s = 0; phase ^= 1u; }
       }
       if (PAIR) umma_commit_pair(accum_bar); else umma_commit(accum_bar);     // accumulators complete
+    } else if (PAIR && lane == 0) {
+      // ---- relay (non-leader CTA of a pair): A tile complete -> proxy fence on THIS SM -> one arrive on the leader ----
+      int s = 0;
+      uint32_t phase = 0;
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (a.pad_ & 1) mbar_wait(&full_bar[s], phase); else mbar_wait_relaxed(&full_bar[s], phase);
+        fence_proxy_async_smem();
+        mbar_arrive_remote(full_leader + (uint32_t)s * 8u);
+        if (++s == stages) { s = 0; phase ^= 1u; }
+      }
     }
     __syncwarp();
   }
@@ -593,14 +601,33 @@ int make_plan(const StmDcnConv* conv, const DcnParams& p, TcPlan* out) {
   // < 113 KB shared memory each), so one CTA's prologue / epilogue hides behind the other's main loop
   // (B200: 0.358 -> 0.323 ms on the 48x80 C=128 layers).  With N = 256 the doubled weight traffic costs more.
   pl.two_ctas = pl.block_n <= 128 && pl.block_n >= 64 && !pl.plain;
+  // N = 256 with enough rows to put two 128-row CTAs on every SM: two 8-warp CTAs per SM, each the half of a
+  // cta_group::2 PAIR with a CTA on the neighbouring SM (so it keeps only 128 of the 256 weight rows: 32 KB per
+  // stage, 80 KB per CTA, 256 TMEM columns).  One CTA's prologue / epilogue and the pair's lock-step stalls hide
+  // behind the other CTA's main loop (B200, FCB 3x5 over P3..P7, 72 frames: 1.008 -> 0.965 ms; 256-row pairs
+  // with the same two stages: 1.055 ms, with three stages and less L1: 1.005 ms).
+  const int64_t ctas128 = ((rows + 127) / 128) * pl.n_tiles;
+  bool pair2 = pl.block_n == 256 && !pl.plain && ctas128 >= 2 * device_sm_count();
   if (pl.two_ctas) pl.m_tiles = 1;
   // explicit, stateless overrides (tests force every CTA shape through the same entry point)
+  if ((conv->flags & (STM_DCN_HINT_ROWS128 | STM_DCN_HINT_ROWS256 | STM_DCN_HINT_NO_PAIR)) != 0) pair2 = false;
   if ((conv->flags & STM_DCN_HINT_ROWS128) != 0) { pl.m_tiles = 1; pl.two_ctas = false; }
   if ((conv->flags & STM_DCN_HINT_ROWS256) != 0 && 2 * pl.block_n <= 512) { pl.m_tiles = 2; pl.two_ctas = false; }
+  if ((conv->flags & STM_DCN_HINT_TWO_CTAS) != 0 && !pl.plain && pl.block_n >= 64) {
+    pl.m_tiles = 1;
+    pl.two_ctas = true;
+    pair2 = pl.block_n >= 128 && (conv->flags & STM_DCN_HINT_NO_PAIR) == 0;
+  }
+  if (pair2) { pl.m_tiles = 1; pl.two_ctas = true; }
   pl.pw = pl.two_ctas ? 8 : 16;
-  // CTA pairs (tcgen05 cta_group::2): each CTA fetches and keeps only half of the N tile's weights.  Pays when the
-  // B operand is a large share of the shared-memory traffic (N >= 128) and the launch fills the GPU with pairs.
-  pl.pair = !pl.two_ctas && pl.block_n >= 128 && pl.block_n % 32 == 0 && (conv->flags & STM_DCN_HINT_NO_PAIR) == 0;
+  // CTA pairs (tcgen05 cta_group::2): each CTA fetches and keeps only half of the N tile's weights.  On their own
+  // (one 256-row CTA per SM) they measured no faster than unpaired CTAs — the kernel is bound by gather latency,
+  // not by shared-memory bandwidth, although the pair does cut the tensor core's shared-memory reads by a third
+  // (profiles/r02_dcn_pair_vs_single.txt) — so they are used where they let two CTAs share an SM, and for the
+  // plain-conv mode with wide N; STM_DCN_HINT_ROWS256 / _ROWS128 without _NO_PAIR still select them for the tests.
+  const bool hinted_rows = (conv->flags & (STM_DCN_HINT_ROWS128 | STM_DCN_HINT_ROWS256)) != 0;
+  pl.pair = (pair2 || (!pl.two_ctas && (hinted_rows || pl.plain) && pl.block_n >= 128)) && pl.block_n % 32 == 0 &&
+            (conv->flags & STM_DCN_HINT_NO_PAIR) == 0;
   const int rows_per_cta = TILE_M * pl.m_tiles;
   pl.blocks = 0;
   for (int i = 0; i < p.n_probs; ++i) pl.blocks += (p.prob[i].m_total + rows_per_cta - 1) / rows_per_cta;
@@ -610,7 +637,7 @@ int make_plan(const StmDcnConv* conv, const DcnParams& p, TcPlan* out) {
   while (cols < pl.m_tiles * pl.block_n) cols <<= 1;
   pl.tmem_cols = cols;
   // pipeline depth: as many stages as fit while leaving L1 some room for the gather's corner reuse
-  int budget = pl.m_tiles == 2 ? 172 * 1024 : (pl.two_ctas ? 110 * 1024 : 132 * 1024);
+  int budget = pl.m_tiles == 2 ? 172 * 1024 : (pl.two_ctas ? (pl.pair ? 82 * 1024 : 110 * 1024) : 132 * 1024);
   if ((conv->flags & STM_DCN_HINT_DEEP_PIPE) != 0) budget = 200 * 1024;
   auto total = [&](int st) {
     return pl.m_tiles == 2 ? SmemLayout<2>(pl.block_n, st, pl.pair).total : SmemLayout<1>(pl.block_n, st, pl.pair).total;
@@ -683,7 +710,7 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   if (blocks == 0) return STM_OK;
   args.block_n = pl.block_n;
   args.tmem_cols = pl.tmem_cols;
-  args.pad_ = 0;
+  args.pad_ = (conv->flags >> 20) & 0xff;      // experiment bits (profiling only; undocumented, results identical)
   args.stages = pl.stages;
 
   CUtensorMap tmap;
@@ -707,7 +734,7 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
     STM_GO(1, 16, 2, false, true);
   }
   if (pl.m_tiles == 2) { if (pl.pair) STM_GO(2, 16, 2, true, false); STM_GO(2, 16, 2, false, false); }
-  if (pl.pw == 8) STM_GO(1, 8, 2, false, false);            // 4 gather tasks per thread per K block, two CTAs per SM
+  if (pl.pw == 8) { if (pl.pair) STM_GO(1, 8, 2, true, false); STM_GO(1, 8, 2, false, false); }   // 4 gather tasks per thread per K block, two CTAs per SM
   if (pl.pair) STM_GO(1, 16, 2, true, false);
   STM_GO(1, 16, 2, false, false);                           // 2 tasks
 #undef STM_GO

@@ -82,35 +82,13 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on a barrier of ANOTHER CTA of the cluster (address from map_to_cta); release at cluster scope so the
-// arriving warp's shared-memory writes are visible to the waiter in the other CTA
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Arrive on a barrier of ANOTHER CTA of the cluster (address from map_to_cta).  Default semantics (release at CTA
+// scope) on purpose: a cluster-scope release compiles to MEMBAR.ALL.GPU and a cluster-scope acquire on the waiting
+// side to CCTL.IVALL (an L1 flush) — per K block that costs far more than the pairing saves.  Only the SIGNAL
+// crosses CTAs here; the data it covers never does (see dcn_tc.cu, PAIR).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// single-thread waiter on a barrier that CTAs of the whole cluster arrive on
-__device__ __forceinline__ void mbar_wait_relaxed_cluster(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    __nanosleep(64);
-    if ((++spins & 0xffu) == 0 && clock64() - t0 > STM_MBAR_TIMEOUT_CYCLES) __trap();
-  }
-}
-// generic-proxy writes (any CTA of the cluster, acquired by this thread) -> visible to the async proxy
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

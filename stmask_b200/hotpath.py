@@ -257,6 +257,7 @@ class HotPath(torch.nn.Module):
         io.s_out.synchronize()
         io.s_comp.synchronize()
 
+    @torch.no_grad()
     def _frames_only(self, inp):
         """Backbone DCN + FCB of a batch of frames (per-frame independent operators)."""
         out = {}
@@ -269,6 +270,7 @@ class HotPath(torch.nn.Module):
                 out[f"fcb.y{l}.{k}"] = y
         return out
 
+    @torch.no_grad()
     def _tf_only(self, inp, plan, rank, group):
         """Temporal fusion of every local frame pair (halo exchange included); ONE [pairs, 633, H, W] result."""
         n = inp["tf.fpn"].shape[0]

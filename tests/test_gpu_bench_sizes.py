@@ -41,7 +41,8 @@ def _variants_to_check(ops, L, shapes, spec):
     auto = ops.deform_conv2d_variant(shapes, spec, BF16)
     out = [(0, auto)]
     for hint in (L.DCN_HINT_NO_PAIR, L.DCN_HINT_ROWS128, L.DCN_HINT_ROWS128 | L.DCN_HINT_NO_PAIR, L.DCN_HINT_ROWS256,
-                 L.DCN_HINT_ROWS256 | L.DCN_HINT_NO_PAIR):
+                 L.DCN_HINT_ROWS256 | L.DCN_HINT_NO_PAIR, L.DCN_HINT_DEEP_PIPE, L.DCN_HINT_TWO_CTAS,
+                 L.DCN_HINT_TWO_CTAS | L.DCN_HINT_NO_PAIR):
         v = ops.deform_conv2d_variant(shapes, spec, BF16, hint=hint)
         if all(v != o[1] for o in out):
             out.append((hint, v))
@@ -69,7 +70,9 @@ def test_fcb_sweep_grouped_launch_vs_oracle(cuda_device, kernel, dg):
     od = [dev(o, torch.float32, cuda_device, cl=False) for o in offs]
     shapes = [tuple(x.shape) for x in xs]
     checked = _variants_to_check(ops, L, shapes, spec)
-    assert "tcgen05" in checked[0][1] and "rows=256" in checked[0][1], checked[0][1]     # 40 920 rows: the bench instantiation
+    # 40 920 rows: the bench instantiation (two 128-row CTAs per SM, each half of a cta_group::2 pair)
+    assert "tcgen05 rows=128 n=256 pair=1" in checked[0][1] and "ctas_per_sm=2" in checked[0][1], checked[0][1]
+    assert any("rows=256" in v and "pair=0" in v for _, v in checked) and any("rows=256" in v and "pair=1" in v for _, v in checked), checked
     assert len(checked) >= 2, checked
     for hint, variant in checked:
         ys = ops.deform_conv2d_multi(xd, od, None, wp, None, spec, relu=True, hint=hint)
@@ -84,10 +87,13 @@ def test_fcb_sweep_grouped_launch_vs_oracle(cuda_device, kernel, dg):
 # ------------------------------------------------------------------------------------------
 BACKBONE = [
     # C,  H,  W, stride, frames, expected in variant
-    (256, 48, 80, 2, 20, "rows=256 n=256"),      # layer3 block 0 (s2): 19 200 rows >= 18 944
-    (256, 24, 40, 1, 20, "rows=256 n=256"),      # layer3
-    (512, 24, 40, 2, 40, "rows=256 n=256"),      # layer4 block 0: two N tiles, 9 600 rows >= 9 472
-    (512, 12, 20, 1, 40, "rows=256 n=256"),
+    (256, 48, 80, 2, 20, "rows=256 n=256 pair=0"),     # layer3 block 0 (s2): 19 200 rows >= 18 944
+    (256, 24, 40, 1, 20, "rows=256 n=256 pair=0"),     # layer3
+    (256, 24, 40, 1, 40, "rows=128 n=256 pair=1"),     # layer3 at >= 37 888 rows (the 72-frame bench): paired two-CTA shape
+    (256, 48, 80, 2, 40, "rows=128 n=256 pair=1"),
+    (512, 24, 40, 2, 40, "rows=256 n=256 pair=0"),     # layer4 block 0: two N tiles, 9 600 rows >= 9 472
+    (512, 12, 20, 1, 40, "rows=256 n=256 pair=0"),
+    (512, 12, 20, 1, 80, "rows=128 n=256 pair=1"),     # layer4 at 19 200 rows x 2 N tiles (c5 workload sizes)
     (128, 48, 80, 1, 8, "rows=128 n=128"),       # layer2: two 8-warp CTAs per SM
     (128, 96, 160, 2, 6, "rows=128 n=128"),      # layer2 block 0 (s2)
 ]

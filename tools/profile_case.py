@@ -19,6 +19,7 @@ ap.add_argument("--frames", type=int, default=72)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--backend", default="auto")
 ap.add_argument("--offset-scale", type=float, default=2.0)
+ap.add_argument("--hint", type=int, default=0, help="STM_DCN_HINT_* bits (16 rows128, 32 rows256, 64 no-pair, 256 deep pipe)")
 a = ap.parse_args()
 dev = "cuda"
 torch.manual_seed(0)
@@ -58,9 +59,10 @@ if a.case.startswith("fcb"):
     lv = fpn_level_sizes()
     xs = [torch.randn(F, 256, h, ww, device=dev).bfloat16().contiguous(memory_format=torch.channels_last) for h, ww in lv]
     offs = [torch.randn(F, 2 * kh * kw, h, ww, device=dev) * a.offset_scale for h, ww in lv]
-    outs = ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=a.backend)
+    outs = ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=a.backend, hint=a.hint)
     px = sum(h * ww for h, ww in lv)
-    timeit(lambda: ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=a.backend, outs=outs),
+    print(ops.deform_conv2d_variant([tuple(x.shape) for x in xs], spec, torch.bfloat16, a.backend, a.hint))
+    timeit(lambda: ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=a.backend, outs=outs, hint=a.hint),
            flops=2.0 * F * px * 256 * 256 * kh * kw)
 elif a.case.startswith("bb"):
     C, H, W, s = {"bb128s2": (128, 96, 160, 2), "bb128": (128, 48, 80, 1), "bb256s2": (256, 48, 80, 2), "bb256": (256, 24, 40, 1),
@@ -70,11 +72,19 @@ elif a.case.startswith("bb"):
     w = (torch.randn(C, C, 3, 3, device=dev) / (C * 9) ** 0.5).bfloat16()
     wp = ops.pack_weight(w, spec, torch.bfloat16)
     x = torch.randn(F, C, H, W, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
-    om = (torch.randn(F, 27, Ho, Wo, device=dev) * (a.offset_scale / 2.0)).bfloat16()
+    om = (torch.randn(F, 32, Ho, Wo, device=dev) * (a.offset_scale / 2.0)).contiguous(memory_format=torch.channels_last)   # fp32, as the predictor writes it
     bias = torch.randn(C, device=dev)
-    outs = ops.deform_conv2d_multi([x], [om[:, :18]], [om[:, 18:]], wp, bias, spec, mask_sigmoid=True, backend=a.backend)
-    timeit(lambda: ops.deform_conv2d_multi([x], [om[:, :18]], [om[:, 18:]], wp, bias, spec, mask_sigmoid=True, backend=a.backend, outs=outs),
+    outs = ops.deform_conv2d_multi([x], [om[:, :18]], [om[:, 18:27]], wp, bias, spec, mask_sigmoid=True, backend=a.backend, hint=a.hint)
+    print(ops.deform_conv2d_variant([tuple(x.shape)], spec, torch.bfloat16, a.backend, a.hint))
+    timeit(lambda: ops.deform_conv2d_multi([x], [om[:, :18]], [om[:, 18:27]], wp, bias, spec, mask_sigmoid=True, backend=a.backend, outs=outs, hint=a.hint),
            flops=2.0 * F * Ho * Wo * C * C * 9)
+    # its offset / mask-logit predictor: the plain-conv mode of the same main loop, fp32 output
+    pc = ops.PlainConv()
+    cw = (torch.randn(27, C, 3, 3, device=dev) * 0.02).bfloat16()
+    cb = torch.randn(27, device=dev).bfloat16()
+    pc([x], cw, cb, s, 1, 1, out_f32=True)
+    a.case += ".predictor"
+    timeit(lambda: pc([x], cw, cb, s, 1, 1, out_f32=True), flops=2.0 * F * Ho * Wo * C * 32 * 9)
 elif a.case == "corr":
     n = F - 1
     x1 = torch.randn(n, 256, 24, 40, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
