@@ -71,7 +71,7 @@ class DCN(DCNv2):
         self.conv_offset_mask.weight.data.zero_()
         self.conv_offset_mask.bias.data.zero_()
 
-    def forward(self, input):
+    def forward(self, input, out=None):
         # The original does conv_offset_mask -> chunk -> cat(o1, o2) -> sigmoid(mask) -> dcn_v2_conv.  Here the
         # predictor is this library's own regular convolution (zero-offset mode of the same tcgen05 main loop)
         # with the bias fused and the fp32 accumulators stored as fp32: sampling positions are never rounded to
@@ -81,8 +81,9 @@ class DCN(DCNv2):
         n_off = 2 * self.deformable_groups * self.kernel_size[0] * self.kernel_size[1]
         n_all = n_off + n_off // 2
         com = self.conv_offset_mask
-        out = self._predictor([input], com.weight, com.bias, com.stride, com.padding, com.dilation, out_f32=True)[0]
+        om = self._predictor([input], com.weight, com.bias, com.stride, com.padding, com.dilation, out_f32=True)[0]
         spec = self._spec()
-        return ops.deform_conv2d_multi([input], [out[:, :n_off]], [out[:, n_off:n_all]],
+        return ops.deform_conv2d_multi([input], [om[:, :n_off]], [om[:, n_off:n_all]],
                                        self._cache.weight(self.weight, spec, input.dtype),
-                                       self._cache.bias(self.bias), spec, mask_sigmoid=True)[0]
+                                       self._cache.bias(self.bias), spec, mask_sigmoid=True,
+                                       outs=None if out is None else [out])[0]

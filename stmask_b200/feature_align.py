@@ -11,7 +11,7 @@ B200-specific additions:
 """
 from __future__ import annotations
 
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 import torch.nn as nn
@@ -49,13 +49,14 @@ class FeatureAlign(nn.Module):
             raise ValueError("FCB(ali) offsets are defined for deformable_groups == 1 (Featurealign.py:67-69)")
         return ops.fcb_ali_offsets(shape.detach(), self.kernel_size)
 
-    def calibrate_levels(self, xs: Sequence[torch.Tensor], shapes: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    def calibrate_levels(self, xs: Sequence[torch.Tensor], shapes: Sequence[torch.Tensor],
+                         outs: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
         """relu(conv_adaption(x, offset)) for every level, one launch."""
         ops._no_grad_inputs(self.conv_adaption.weight, *xs)
         offs = [self.offsets(s) for s in shapes]
         spec = self.conv_adaption.spec()
         wp = self.conv_adaption._cache.weight(self.conv_adaption.weight, spec, xs[0].dtype)
-        return ops.deform_conv2d_multi(list(xs), offs, None, wp, None, spec, relu=True)
+        return ops.deform_conv2d_multi(list(xs), offs, None, wp, None, spec, relu=True, outs=outs)
 
     def forward_levels(self, xs: Sequence[torch.Tensor], shapes: Sequence[torch.Tensor]) -> List[torch.Tensor]:
         return [self.conv(y) for y in self.calibrate_levels(xs, shapes)]

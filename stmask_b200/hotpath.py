@@ -72,21 +72,60 @@ class HotPathConfig:
         return f"{'R101' if self.backbone == 'r101' else 'R50'}-DCN-FPN " + "+".join(parts)
 
 
+class SlabLayout:
+    """Byte layout of ONE pinned-host / device slab holding, for a chunk of `n` frames, every tensor of `shapes`
+    back to back (each as NHWC-contiguous [n, H, W, C]): one host<->device copy per chunk and direction instead of
+    one per tensor (r1: ~60 small copies per chunk reached 34 GB/s; one slab reaches the link's rate)."""
+
+    def __init__(self, shapes: Dict[str, Tuple[Tuple[int, int, int], torch.dtype]], n: int):
+        self.n = n
+        self.fields = []                 # (key, (C, H, W), dtype, byte offset, byte length)
+        off = 0
+        for k, ((c, h, w), dt) in shapes.items():
+            nb = n * c * h * w * torch.empty((), dtype=dt).element_size()
+            self.fields.append((k, (c, h, w), dt, off, nb))
+            off += (nb + 255) // 256 * 256
+        self.nbytes = off
+
+    def views(self, slab: torch.Tensor, n: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """NCHW-shaped channels-last views [n, C, H, W] into a uint8 slab (first n frames of every field)."""
+        n = self.n if n is None else n
+        out = {}
+        for k, (c, h, w), dt, off, nb in self.fields:
+            es = torch.empty((), dtype=dt).element_size()
+            t = slab[off:off + n * c * h * w * es].view(dt).view(n, h, w, c).permute(0, 3, 1, 2)
+            out[k] = t
+        return out
+
+
 class StreamedIO:
-    """Streams and device staging buffers of `HotPath.forward_streamed` (allocated once, reused every step)."""
+    """Streams, slab layouts and double-buffered device staging of `HotPath.forward_streamed`."""
 
-    def __init__(self, device, chunk_frames: int = 12):
+    def __init__(self, hp: "HotPath", device, n_frames: int, chunk_frames: int = 16):
         self.device = device
-        self.chunk_frames = chunk_frames
+        self.chunk = chunk_frames
+        self.n = n_frames
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(device) for _ in range(3))
-        self._d_in: Dict[str, torch.Tensor] = {}
+        fin, fout, tin, tout = hp.io_shapes()
+        self.lin, self.lout = SlabLayout(fin, chunk_frames), SlabLayout(fout, chunk_frames)
+        self.tin, self.tout = SlabLayout(tin, n_frames), None
+        self.tout_shapes = tout
+        self.d_in = [torch.empty(self.lin.nbytes, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.d_out = [torch.empty(self.lout.nbytes, dtype=torch.uint8, device=device) for _ in range(2)]
+        self.d_tin = torch.empty(max(self.tin.nbytes, 1), dtype=torch.uint8, device=device)
+        self.free_in = [torch.cuda.Event() for _ in range(2)]      # compute finished reading d_in[i]
+        self.free_out = [torch.cuda.Event() for _ in range(2)]     # D2H finished reading d_out[i]
+        self.n_chunks = (n_frames + chunk_frames - 1) // chunk_frames
 
-    def device_inputs(self, host_in: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        for k, v in host_in.items():
-            t = self._d_in.get(k)
-            if t is None or t.shape != v.shape or t.dtype != v.dtype:
-                self._d_in[k] = torch.empty_like(v, device=self.device)      # keeps the channels-last strides
-        return self._d_in
+    def host_buffers(self, n_pairs: int):
+        """Pinned host slabs: inputs / outputs per chunk, temporal-fusion inputs (all frames) and result."""
+        pin = lambda nb: torch.empty(max(nb, 1), dtype=torch.uint8).pin_memory()
+        h_in = [pin(self.lin.nbytes) for _ in range(self.n_chunks)]
+        h_out = [pin(self.lout.nbytes) for _ in range(self.n_chunks)]
+        h_tin = pin(self.tin.nbytes)
+        self.tout = SlabLayout(self.tout_shapes, n_pairs) if self.tout_shapes and n_pairs > 0 else None
+        h_tout = pin(self.tout.nbytes) if self.tout is not None else None
+        return h_in, h_out, h_tin, h_tout
 
 
 class HotPath(torch.nn.Module):
@@ -141,13 +180,18 @@ class HotPath(torch.nn.Module):
         return st
 
     # ---------------------------------------------------------------- synthetic activations
-    def make_inputs(self, n_frames: int, device, seed: int = 0, pinned_host: bool = False) -> Dict[str, torch.Tensor]:
+    def make_inputs(self, n_frames: int, device, seed: int = 0, pinned_host: bool = False,
+                    on_device: bool = False) -> Dict[str, torch.Tensor]:
         """Synthetic N(0,1) activations of the shapes the reference produces for `n_frames` frames
-        (NHWC memory, cfg.dtype); box deltas N(0,1) fp32."""
-        g = torch.Generator().manual_seed(1000 + seed)
+        (NHWC memory, cfg.dtype); box deltas N(0,1) fp32.  `on_device`: draw them with the device's generator
+        (the 1024-frame workload is 15 GB of inputs; the host generator would take minutes)."""
+        g = torch.Generator(device=device if on_device else "cpu").manual_seed(1000 + seed)
         dt = self.cfg.dtype
 
         def mk(shape, dtype):
+            if on_device:
+                n, c, h, w = shape
+                return torch.randn((n, h, w, c), generator=g, dtype=dtype, device=device).permute(0, 3, 1, 2)
             t = torch.randn(shape, generator=g, dtype=torch.float32).to(dtype).contiguous(memory_format=torch.channels_last)
             if pinned_host:
                 return t.pin_memory()
@@ -208,65 +252,89 @@ class HotPath(torch.nn.Module):
         return out
 
     # ---------------------------------------------------------------- end to end from host memory
+    def io_shapes(self):
+        """Per-frame (C, H, W) / dtype of every per-frame input and output, and of the temporal-fusion inputs / result."""
+        dt = self.cfg.dtype
+        fin, fout, tin, tout = {}, {}, {}, {}
+        for i, s in enumerate(self.dcn_shapes):
+            fin[f"dcn{i}.x"] = ((s.channels, s.in_h, s.in_w), dt)
+            fout[f"dcn{i}.y"] = ((s.channels, s.out_h, s.out_w), dt)
+        if self.cfg.fcb:
+            for l, (h, w) in enumerate(self.level_sizes):
+                fin[f"fcb.x{l}"] = ((FPN_CHANNELS, h, w), dt)
+                for k in range(len(HEAD_KERNELS)):
+                    fin[f"fcb.box{l}.{k}"] = ((4, h, w), torch.float32)
+                    fout[f"fcb.y{l}.{k}"] = ((FPN_CHANNELS, h, w), dt)
+        if self.cfg.temporal_fusion:
+            h, w = self.level_sizes[CORR_LEVEL]
+            tin["tf.fpn"] = ((FPN_CHANNELS, h, w), dt)
+            tin["tf.t2s"] = ((FPN_CHANNELS, h, w), dt)
+            from .temporal_fusion import padded_corr_channels
+            tout["tf.concat"] = ((padded_corr_channels(CORR_PATCH) + 2 * FPN_CHANNELS, h, w), dt)
+        return fin, fout, tin, tout
+
     @torch.no_grad()
-    def forward_streamed(self, host_in: Dict[str, torch.Tensor], host_out: Dict[str, torch.Tensor], io: "StreamedIO",
-                         plan: Optional[sharding.ShardPlan] = None, rank: int = 0, group=None) -> None:
-        """The same step as `forward`, fed from PINNED HOST tensors and delivering every result into pinned
-        host tensors (`host_out`, keyed like `forward`'s result; one `tf.concat` per call).  The frame batch
-        is cut into chunks; host->device copies, kernels and device->host copies of consecutive chunks run
-        on three streams, so the PCIe transfers in both directions overlap each other and the compute.
-        Temporal fusion goes first (its inputs are small and every later chunk is independent of it)."""
-        n = next(iter(host_in.values())).shape[0]
-        d_in = io.device_inputs(host_in)
-        keep = []                                            # results stay referenced until the final sync
-
-        def h2d(keys, a, b, ev):
+    def forward_streamed(self, host, io: "StreamedIO", plan: Optional[sharding.ShardPlan] = None, rank: int = 0, group=None) -> None:
+        """The same step as `forward`, fed from PINNED HOST slabs and delivering every result into pinned host
+        slabs.  `host` = (h_in, h_out, h_tin, h_tout) from `io.host_buffers()`: per chunk of `io.chunk` frames ONE
+        input slab and ONE output slab (`io.lin` / `io.lout` give the tensor views), plus one slab with the
+        temporal-fusion inputs of all frames and one for its result.  Per chunk: one H2D copy, the kernels (writing
+        straight into the output slab's views), one D2H copy; the three run on three streams with double-buffered
+        device slabs, so both PCIe directions and the compute overlap.  Temporal fusion goes first (its inputs are
+        small and every later chunk is independent of it)."""
+        h_in, h_out, h_tin, h_tout = host
+        keep = []
+        if self.cfg.temporal_fusion and io.tin.nbytes:
+            ev_in, ev_done = torch.cuda.Event(), torch.cuda.Event()
             with torch.cuda.stream(io.s_in):
-                for k in keys:
-                    d_in[k][a:b].copy_(host_in[k][a:b], non_blocking=True)
-                ev.record(io.s_in)
-
-        def d2h(pairs, ev):
+                io.d_tin.copy_(h_tin, non_blocking=True)
+                ev_in.record(io.s_in)
+            with torch.cuda.stream(io.s_comp):
+                io.s_comp.wait_event(ev_in)
+                sub = self._tf_only(io.tin.views(io.d_tin), plan, rank, group)
+                ev_done.record(io.s_comp)
+            if sub:
+                t = sub["tf.concat"]
+                keep.append(t)
+                with torch.cuda.stream(io.s_out):
+                    io.s_out.wait_event(ev_done)
+                    t.record_stream(io.s_out)
+                    io.tout.views(h_tout)["tf.concat"].copy_(t, non_blocking=True)
+        for ci in range(io.n_chunks):
+            a = ci * io.chunk
+            nf = min(io.n, a + io.chunk) - a
+            buf = ci & 1
+            ev_in, ev_done = torch.cuda.Event(), torch.cuda.Event()
+            with torch.cuda.stream(io.s_in):
+                io.s_in.wait_event(io.free_in[buf])              # the kernels of chunk ci-2 have read this device slab
+                io.d_in[buf].copy_(h_in[ci], non_blocking=True)
+                ev_in.record(io.s_in)
+            with torch.cuda.stream(io.s_comp):
+                io.s_comp.wait_event(ev_in)
+                io.s_comp.wait_event(io.free_out[buf])           # the D2H of chunk ci-2 has drained this output slab
+                self._frames_only(io.lin.views(io.d_in[buf], nf), outs=io.lout.views(io.d_out[buf], nf))
+                io.free_in[buf].record(io.s_comp)
+                ev_done.record(io.s_comp)
             with torch.cuda.stream(io.s_out):
-                io.s_out.wait_event(ev)
-                for dst, src in pairs:
-                    src.record_stream(io.s_out)
-                    dst.copy_(src, non_blocking=True)
-
-        tf_keys = [k for k in host_in if k.startswith("tf.")]
-        frame_keys = [k for k in host_in if not k.startswith("tf.")]
-        if tf_keys:
-            ev_in, ev_done = torch.cuda.Event(), torch.cuda.Event()
-            h2d(tf_keys, 0, n, ev_in)
-            with torch.cuda.stream(io.s_comp):
-                io.s_comp.wait_event(ev_in)
-                sub = self._tf_only({k: d_in[k] for k in tf_keys}, plan, rank, group)
-                ev_done.record(io.s_comp)
-            keep.append(sub)
-            d2h([(host_out[k], v) for k, v in sub.items()], ev_done)
-        for a in range(0, n, io.chunk_frames):
-            b = min(n, a + io.chunk_frames)
-            ev_in, ev_done = torch.cuda.Event(), torch.cuda.Event()
-            h2d(frame_keys, a, b, ev_in)
-            with torch.cuda.stream(io.s_comp):
-                io.s_comp.wait_event(ev_in)
-                sub = self._frames_only({k: d_in[k][a:b] for k in frame_keys})
-                ev_done.record(io.s_comp)
-            keep.append(sub)
-            d2h([(host_out[k][a:b], v) for k, v in sub.items()], ev_done)
+                io.s_out.wait_event(ev_done)
+                h_out[ci].copy_(io.d_out[buf], non_blocking=True)
+                io.free_out[buf].record(io.s_out)
         io.s_out.synchronize()
         io.s_comp.synchronize()
 
     @torch.no_grad()
-    def _frames_only(self, inp):
-        """Backbone DCN + FCB of a batch of frames (per-frame independent operators)."""
+    def _frames_only(self, inp, outs: Optional[Dict[str, torch.Tensor]] = None):
+        """Backbone DCN + FCB of a batch of frames (per-frame independent operators).  `outs`: preallocated
+        channels-last result tensors (views of an output slab) the kernels write into directly."""
         out = {}
         for i, m in enumerate(self.backbone_dcn):
-            out[f"dcn{i}.y"] = m(inp[f"dcn{i}.x"])
+            out[f"dcn{i}.y"] = m(inp[f"dcn{i}.x"], out=None if outs is None else outs[f"dcn{i}.y"])
+        nl = len(self.level_sizes)
         for k, m in enumerate(self.fcb):
-            xs = [inp[f"fcb.x{l}"] for l in range(len(self.level_sizes))]
-            boxes = [inp[f"fcb.box{l}.{k}"] for l in range(len(self.level_sizes))]
-            for l, y in enumerate(m.calibrate_levels(xs, boxes)):
+            xs = [inp[f"fcb.x{l}"] for l in range(nl)]
+            boxes = [inp[f"fcb.box{l}.{k}"] for l in range(nl)]
+            ys = m.calibrate_levels(xs, boxes, outs=None if outs is None else [outs[f"fcb.y{l}.{k}"] for l in range(nl)])
+            for l, y in enumerate(ys):
                 out[f"fcb.y{l}.{k}"] = y
         return out
 
