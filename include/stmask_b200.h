@@ -13,6 +13,9 @@
  *   stm_fcb_ada_offsets     <- the 1x1 conv_offset on box deltas    (layers/modules/Featurealign.py:20-25,44)
  *   stm_roi_align_fwd       <- mmcv.ops.roi_align as bbox_feat_extractor calls it
  *                              (layers/modules/track_to_segment_head.py:65-88)
+ *   stm_pool_fc_fwd         <- TemporalNet's AvgPool2d(7x7) + fc + fc_coeff tail; its three 3x3 convs are
+ *                              stm_deform_conv2d_fwd with STM_DCN_ZERO_OFFSET
+ *                              (layers/modules/track_to_segment_head.py:10-37)
  *   stm_correlation_fwd     <- spatial_correlation_sampler.spatial_correlation_sample
  *                              + the /C, leaky-ReLU, concat, ReLU that follow it
  *                              (layers/modules/track_to_segment_head.py:53-62,
@@ -243,6 +246,17 @@ typedef struct StmRoiAlignDesc {
  * out[r, c, i, j] = mean over the sample grid of bin (i, j) of the bilinearly interpolated feature;
  * sample points outside [-1, h] x [-1, w] contribute 0, others are clamped into the map. */
 int stm_roi_align_fwd(const StmRoiAlignDesc* desc, const void* feat, const float* rois, void* out, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* TemporalNet tail: y[n, :] = W * mean over the hw pixels of x[n] + b        */
+/* (AvgPool2d(7x7) + fc + fc_coeff, track_to_segment_head.py:17-19,31-35)     */
+/* ------------------------------------------------------------------------- */
+/* x: NHWC activations [n, hw, c] (`dtype`), pixel p of box i at x + i*x_stride_n + p*x_stride_p (elements);
+ * weight: float32 [out_features][c] (fc rows, then fc_coeff rows), bias: float32[out_features] or NULL;
+ * y: float32 [n][out_features]. */
+int stm_pool_fc_fwd(const void* x, int32_t dtype, int32_t n, int32_t hw, int32_t c,
+                    int64_t x_stride_n, int64_t x_stride_p, const float* weight, const float* bias,
+                    int32_t out_features, float* y, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Layout helpers (NCHW <-> NHWC with dtype conversion), used at the module   */

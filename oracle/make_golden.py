@@ -17,6 +17,12 @@ Sources of truth:
   roi_align.npz         torchvision.ops.roi_align (CPU) cases (aligned / legacy, adaptive / fixed sampling grid,
                         boxes over the border) and the reference's own bbox_feat_extractor call site
                         (track_to_segment_head.py:65-88) with its own sanitize_coordinates_hw
+  model_r50.npz         BASELINE.json configs[0]: the reference's own STMask (R50-DCN-FPN FCA+TF, STMask.py:205-329) on a
+                        synthetic 2-frame clip via oracle/ref_model.py: inputs / outputs of all 7 backbone DCN call sites,
+                        the correlate / concat / RoIAlign / TemporalNet call sites of CandidateShift and the shifted boxes
+  temporal_net.npz      the reference's own TemporalNet.forward + bbox_feat_extractor (track_to_segment_head.py:10-37,
+                        65-88) on a 633-channel concat; the 40 MB of weights are rebuilt from the recorded seed
+                        (default nn init in construction order) and pinned by per-parameter checksums
   backbone_dcn.npz      the reference's ResNetBackbone DCN placement (backbone.py:105-138) for the R50/R101
                         configs, and a Bottleneck DCN-branch forward (backbone.py:20-26,45)
 """
@@ -250,6 +256,50 @@ def _roi_align():
     np.savez_compressed(os.path.join(OUT, "roi_align.npz"), **out)
 
 
+TEMPORAL_NET_SEED = 20260117
+
+
+def temporal_net_weight_checksums(net) -> np.ndarray:
+    """[sum, sum of |.|] of every parameter in state_dict order: the GPU test rebuilds the weights from the seed
+    (they are 40 MB — too big for a fixture) and must get exactly these."""
+    return np.array([[float(v.double().sum()), float(v.double().abs().sum())] for v in net.state_dict().values()], np.float64)
+
+
+def _temporal_net():
+    """The reference's own TemporalNet.forward (track_to_segment_head.py:10-37) on 7x7 crops that its own
+    bbox_feat_extractor (:65-88) cut out of a 633-channel concat (TF_utils.py:28-36)."""
+    t2s = rh.load_track_to_segment_head()
+    torch.manual_seed(TEMPORAL_NET_SEED)
+    net = t2s.TemporalNet(633)            # default nn.Conv2d / nn.Linear init in construction order: conv1, conv2, conv3, fc, fc_coeff
+    net.eval()
+    g = torch.Generator().manual_seed(7)
+    q = lambda t: t.bfloat16().float()    # exactly representable in bf16, so the bf16 device path sees the same inputs
+    concat = torch.relu(q(torch.randn(2, 633, 12, 20, generator=g)))
+    boxes = torch.rand(5, 4, generator=g)
+    boxes = torch.stack([boxes[:, 0] * 0.6, boxes[:, 1] * 0.6, boxes[:, 0] * 0.6 + 0.1 + boxes[:, 2] * 0.3,
+                         boxes[:, 1] * 0.6 + 0.1 + boxes[:, 3] * 0.3], 1)
+    pair = torch.tensor([0, 0, 1, 1, 1])
+    with torch.no_grad():
+        crops = torch.cat([t2s.bbox_feat_extractor(concat[int(p)], boxes[i:i + 1], 12, 20, 7) for i, p in enumerate(pair)], 0)
+        x_reg, x_coeff = net(crops)
+        # intermediate activations, for localising a mismatch
+        h1 = torch.relu(net.conv1(crops))
+    np.savez_compressed(os.path.join(OUT, "temporal_net.npz"), seed=np.int64(TEMPORAL_NET_SEED),
+                        checksums=temporal_net_weight_checksums(net), concat=concat.numpy().astype(np.float16) if False else concat.numpy(),
+                        boxes=boxes.numpy(), pair=pair.numpy(), crops=crops.numpy(), x_reg=x_reg.numpy(), x_coeff=x_coeff.numpy(),
+                        h1_mean=h1.mean(dim=(2, 3)).numpy())
+
+
+def _model_r50():
+    """BASELINE.json configs[0] / SURVEY.md 8(c) "Model:" known answer: the reference's own STMask (R50-DCN-FPN
+    FCA+TF) on a synthetic 2-frame clip through oracle/ref_model.py; every hot-op call site of frame 2."""
+    from . import ref_model
+    out = ref_model.run_two_frame_clip()
+    keep = dict(out)
+    keep["roi.out"] = out["roi.out"][:8]              # 8 of the 43 crops (5 MB otherwise); TemporalNet outputs are kept for all
+    np.savez_compressed(os.path.join(OUT, "model_r50.npz"), **keep)
+
+
 def main():
     if not rh.available():
         raise SystemExit("/root/reference is not present: fixtures can only be regenerated in the build container")
@@ -262,6 +312,8 @@ def main():
     _backbone_dcn()
     _detections()
     _roi_align()
+    _temporal_net()
+    _model_r50()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -98,6 +98,8 @@ SIGNATURES = {
                                       C.c_void_p, C.c_void_p]),
     "stm_correlation_backend": (C.c_int, [C.POINTER(StmCorrDesc)]),
     "stm_roi_align_fwd": (C.c_int, [C.POINTER(StmRoiAlignDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "stm_pool_fc_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
+                                  C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "stm_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p]),
     "stm_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -304,6 +304,17 @@ int stm_roi_align_fwd(const StmRoiAlignDesc* d, const void* feat, const float* r
   return launch_roi_align(*d, feat, rois, out, (cudaStream_t)stream);
 }
 
+int stm_pool_fc_fwd(const void* x, int32_t dtype, int32_t n, int32_t hw, int32_t c, int64_t x_stride_n, int64_t x_stride_p,
+                    const float* weight, const float* bias, int32_t out_features, float* y, void* stream) {
+  clear_error();
+  STM_CHECK_ARG(dtype_ok(dtype), "unknown dtype");
+  STM_CHECK_ARG(n >= 0 && hw > 0 && c > 0 && out_features > 0, "bad size");
+  if (n == 0) return STM_OK;
+  STM_CHECK_ARG(x && weight && y, "null pointer");
+  STM_CHECK_ARG(x_stride_p >= c && x_stride_n >= 0, "pixel stride smaller than C");
+  return launch_pool_fc(x, dtype, n, hw, c, x_stride_n, x_stride_p, weight, bias, out_features, y, (cudaStream_t)stream);
+}
+
 int stm_nchw_to_nhwc(const void* src, int32_t sd, void* dst, int32_t dd, int32_t n, int32_t c, int32_t h, int32_t w,
                      void* stream) {
   clear_error();

@@ -130,6 +130,8 @@ int launch_corr_simt(const StmCorrDesc& d, const void* x1, const void* x2, const
 int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const void* fa, const void* fb, void* out,
                    cudaStream_t stream);
 bool corr_tc_supported(const StmCorrDesc& d, const char** why);
+int launch_pool_fc(const void* x, int dtype, int n, int hw, int c, int64_t x_stride_n, int64_t x_stride_p, const float* w,
+                   const float* b, int out_features, float* y, cudaStream_t stream);
 int launch_roi_align(const StmRoiAlignDesc& d, const void* feat, const float* rois, void* out, cudaStream_t stream);
 
 }  // namespace stm

@@ -716,6 +716,30 @@ def roi_align(input: torch.Tensor, rois: torch.Tensor, output_size=7, spatial_sc
     return out
 
 
+def pool_fc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """mean over the spatial positions of x [n, C, h, w] (channels-last memory), then y = W * pooled + b in fp32:
+    the AvgPool2d(7x7) + Linear tail of TemporalNet (track_to_segment_head.py:17-19,31-35).  weight [out, C], bias [out]."""
+    _require_cuda(x, "x")
+    _require_cuda(weight, "weight")
+    if x.dim() != 4:
+        raise ValueError(f"x must be [n, C, h, w], got {tuple(x.shape)}")
+    xn = to_nhwc(x)
+    n, c, h, w = xn.shape
+    if weight.dim() != 2 or weight.shape[1] != c:
+        raise ValueError(f"weight must be [out, {c}], got {tuple(weight.shape)}")
+    if xn.numel() > 0 and xn.stride(2) != w * xn.stride(3):
+        xn = xn.contiguous(memory_format=torch.channels_last)
+    wf = weight.detach().float().contiguous()
+    bf = bias.detach().float().contiguous() if bias is not None else None
+    y = torch.empty((n, wf.shape[0]), dtype=torch.float32, device=x.device)
+    if n == 0:
+        return y
+    with torch.cuda.device(x.device):
+        L.check(L.lib().stm_pool_fc_fwd(xn.data_ptr(), _dt(xn, "x"), n, h * w, c, xn.stride(0), xn.stride(3), wf.data_ptr(),
+                                        bf.data_ptr() if bf is not None else None, wf.shape[0], y.data_ptr(), _stream(x)), "stm_pool_fc_fwd")
+    return y
+
+
 # --------------------------------------------------------------------------------------------
 # torch.library registration (CUDA key only, fake impl for shape inference, no CPU key)
 # --------------------------------------------------------------------------------------------

@@ -1,0 +1,102 @@
+"""BASELINE.json configs[0] — replay of the reference MODEL's hot-op call sites on the GPU (SURVEY.md 8(c) "Model:" KAT).
+
+tests/golden/model_r50.npz holds what the reference's own `STMask.forward` (R50-DCN-FPN FCA+TF, STMask.py:205-329,
+run on the CPU through oracle/ref_model.py over torchvision stand-ins) fed to and got from every operator on the hot
+path for frame 2 of a synthetic 2-frame clip: the 7 backbone `DCN` modules (backbone.py:45), `correlate` /
+`spatial_correlation_sample` (track_to_segment_head.py:53), the concat + ReLU (TF_utils.py:30-31), `roi_align`
+(track_to_segment_head.py:86), `TemporalNet` (TF_utils.py:37) and the shifted boxes.  Each site is replayed through the
+drop-in packages the reference would import (`dcn_v2`, `spatial_correlation_sampler`, `mmcv.ops` from shims/) with
+the same seeded parameters: fp32 <= 1e-4 against the recorded outputs; bf16 <= 1e-2 against the oracle run on
+bf16-rounded inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden, rel_err
+from oracle import ref_model
+
+pytestmark = pytest.mark.gpu
+
+
+def q(a, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dtype).float().numpy()
+
+
+def dev(a, dtype, device, cl=False):
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device=device, dtype=dtype)
+    return t.contiguous(memory_format=torch.channels_last) if cl and t.dim() == 4 else t
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_backbone_dcn_call_sites(cuda_device, dtype):
+    from dcn_v2 import DCN                                   # the reference's import (backbone.py:5), served by shims/
+    z = load_golden("model_r50.npz")
+    assert int(z["n_dcn"]) == 7
+    for i in range(7):
+        x, want = z[f"dcn{i}.x"], z[f"dcn{i}.y"]
+        c, s = x.shape[1], int(z[f"dcn{i}.stride"])
+        w, b, cw, cb = ref_model.seeded_params("dcn", i, [("weight", (c, c, 3, 3)), ("bias", (c,)), ("com_w", (27, c, 3, 3)), ("com_b", (27,))])
+        m = DCN(c, c, kernel_size=3, stride=s, padding=1, dilation=1, deformable_groups=1).to(cuda_device)   # backbone.py:21-22
+        with torch.no_grad():
+            m.weight.copy_(w); m.bias.copy_(b); m.conv_offset_mask.weight.copy_(cw); m.conv_offset_mask.bias.copy_(cb)
+            m = m.to(dtype)
+            y = m(dev(x, dtype, cuda_device)).float().cpu().numpy()
+        if dtype == torch.float32:
+            assert rel_err(y, want) <= 1e-4, (i, rel_err(y, want))
+        else:
+            xr, wr, br, cwr, cbr = (q(t, dtype) for t in (x, w.numpy(), b.numpy(), cw.numpy(), cb.numpy()))
+            ho, wo = want.shape[2:]
+            om = oracle.deform_conv2d(xr, np.zeros((1, 18, ho, wo), np.float32), cwr, cbr, None, stride=s, padding=1)
+            mask = (1.0 / (1.0 + np.exp(-om[:, 18:].astype(np.float64)))).astype(np.float32)
+            ref = oracle.deform_conv2d(xr, om[:, :18], wr, br, mask, stride=s, padding=1)
+            assert rel_err(y, ref) <= 1e-2, (i, rel_err(y, ref))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_temporal_fusion_call_sites(cuda_device, dtype):
+    from mmcv.ops import roi_align                           # track_to_segment_head.py:6
+    from spatial_correlation_sampler import spatial_correlation_sample      # track_to_segment_head.py:4
+    from stmask_b200.temporal_fusion import correlate, correlate_concat
+    from stmask_b200.temporal_net import TemporalNet, shift_candidates
+    z = load_golden("model_r50.npz")
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    x1, x2 = q(z["corr.x1"], dtype), q(z["corr.x2"], dtype)
+    ta, tb = q(z["shift.t2s_ref"], dtype), q(z["shift.t2s_next"], dtype)
+    # correlate(): the reference's call with its keyword arguments
+    out5 = spatial_correlation_sample(dev(x1, dtype, cuda_device), dev(x2, dtype, cuda_device), kernel_size=1, patch_size=11,
+                                      stride=1, padding=0, dilation_patch=1)
+    want5 = z["corr.out5d"] if dtype == torch.float32 else oracle.correlation(x1, x2, 11, 1)
+    assert out5.shape == (1, 11, 11, 6, 10) and rel_err(out5.float().cpu().numpy(), want5) <= tol
+    xc = correlate(dev(x1, dtype, cuda_device), dev(x2, dtype, cuda_device), 11)
+    assert rel_err(xc.float().cpu().numpy(), oracle.correlate(x1, x2, 11, 1)) <= tol
+    # relu(cat[x_corr, T2S_ref, T2S_next]) in one kernel == the tensor the reference handed to bbox_feat_extractor
+    cat = correlate_concat(dev(x1, dtype, cuda_device), dev(x2, dtype, cuda_device), dev(ta, dtype, cuda_device), dev(tb, dtype, cuda_device))
+    want_cat = z["roi.feat"] if dtype == torch.float32 else np.maximum(np.concatenate([oracle.correlate(x1, x2, 11, 1), ta, tb], 1), 0)
+    assert cat.shape == (1, 633, 6, 10) and rel_err(cat.float().cpu().numpy(), want_cat) <= tol
+    # roi_align(feature_maps, rois, 7) as bbox_feat_extractor calls it
+    feat = q(z["roi.feat"], dtype)
+    crops = roi_align(dev(feat, dtype, cuda_device), dev(z["roi.rois"][:8], torch.float32, cuda_device), 7)
+    want_crops = z["roi.out"] if dtype == torch.float32 else oracle.roi_align(feat, z["roi.rois"][:8], 7)
+    assert rel_err(crops.float().cpu().numpy(), want_crops) <= tol
+    # the whole CandidateShift arithmetic on the device: concat (padded layout for bf16) -> RoIAlign -> TemporalNet -> decode
+    torch.manual_seed(ref_model.SEED + 500)
+    net = TemporalNet(633).to(cuda_device)
+    boxes = dev(z["shift.box_ref"], torch.float32, cuda_device)
+    if dtype == torch.bfloat16:
+        net = net.to(dtype)
+        cat = correlate_concat(dev(x1, dtype, cuda_device), dev(x2, dtype, cuda_device), dev(ta, dtype, cuda_device),
+                               dev(tb, dtype, cuda_device), padded=True)
+        assert cat.shape == (1, 640, 6, 10)
+    x_reg, x_coeff = shift_candidates(net, cat, boxes, torch.zeros(boxes.shape[0], dtype=torch.long, device=cuda_device))
+    assert rel_err(x_reg.cpu().numpy(), z["tn.x_reg"]) <= tol, rel_err(x_reg.cpu().numpy(), z["tn.x_reg"])
+    assert rel_err(x_coeff.cpu().numpy(), z["tn.x_coeff"]) <= tol, rel_err(x_coeff.cpu().numpy(), z["tn.x_coeff"])
+    # decode(loc, center_size(box_ref)) (box_utils.py:238-283, TF_utils.py:38): the shifted boxes the tracker consumes
+    b = boxes.cpu()
+    pri = torch.cat([(b[:, 2:] + b[:, :2]) / 2, b[:, 2:] - b[:, :2]], 1)
+    loc = x_reg.cpu()
+    dec = torch.cat([pri[:, :2] + loc[:, :2] * 0.1 * pri[:, 2:], pri[:, 2:] * torch.exp(loc[:, 2:] * 0.2)], 1)
+    dec[:, :2] -= dec[:, 2:] / 2
+    dec[:, 2:] += dec[:, :2]
+    assert np.abs(dec.numpy() - z["shift.box_ref_shift"]).max() <= (1e-5 if dtype == torch.float32 else 2e-3)

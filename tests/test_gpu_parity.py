@@ -664,3 +664,66 @@ def test_pair_indices_are_validated(cuda_device):
     mis = flat[1:1 + 4 * 64 * 6 * 10].view(4, 6, 10, 64).permute(0, 3, 1, 2)     # 2-byte aligned NHWC view
     with pytest.raises(_lib.StmError, match="aligned"):
         ops.correlation_pairs(mis, i32([0, 1]), i32([1, 2]), 11, 1)
+
+
+# ------------------------------------------------------------------------------------------
+# TemporalNet: RoIAlign on the concat buffer -> conv1..3 (plain-conv mode of the tcgen05 main
+# loop) -> AvgPool + fc + fc_coeff, against the reference's own TemporalNet.forward / bbox_feat_extractor
+# ------------------------------------------------------------------------------------------
+def _golden_temporal_net(device):
+    from stmask_b200.temporal_net import TemporalNet
+    z = load_golden("temporal_net.npz")
+    torch.manual_seed(int(z["seed"]))
+    net = TemporalNet(633)                                   # same seed, same construction order as the reference module
+    cs = np.array([[float(v.double().sum()), float(v.double().abs().sum())] for v in net.state_dict().values()])
+    assert np.allclose(cs, z["checksums"], rtol=1e-9, atol=1e-9)       # summation order may differ, the weights may not
+    return z, net.to(device)
+
+
+def test_temporal_net_fp32_vs_reference(cuda_device):
+    from stmask_b200.temporal_net import shift_candidates
+    z, net = _golden_temporal_net(cuda_device)
+    x_reg, x_coeff = net(dev(z["crops"], torch.float32, cuda_device))
+    assert x_reg.shape == (5, 4) and x_coeff.shape == (5, 32)
+    assert rel_err(x_reg.cpu().numpy(), z["x_reg"]) <= 1e-4 and rel_err(x_coeff.cpu().numpy(), z["x_coeff"]) <= 1e-4
+    # with this library's RoIAlign in front (the reference's bbox_feat_extractor call site), reference channel layout
+    x_reg, x_coeff = shift_candidates(net, dev(z["concat"], torch.float32, cuda_device, channels_last=True),
+                                      dev(z["boxes"], torch.float32, cuda_device), torch.from_numpy(z["pair"]).to(cuda_device))
+    assert rel_err(x_reg.cpu().numpy(), z["x_reg"]) <= 1e-4 and rel_err(x_coeff.cpu().numpy(), z["x_coeff"]) <= 1e-4
+
+
+def test_temporal_net_bf16_padded_layout_on_tcgen05(cuda_device):
+    """The hot path's form: the padded 640-channel channels-last concat (as the correlation kernel writes it) ->
+    RoIAlign -> three tcgen05 plain convs -> pool + FC, bf16 storage; <= 1e-2 against the reference's fp32 outputs
+    (inputs are bf16-exact; weights are rounded to bf16 by the module)."""
+    from stmask_b200 import ops
+    from stmask_b200.temporal_net import shift_candidates
+    z, net = _golden_temporal_net(cuda_device)
+    net = net.to(torch.bfloat16)
+    c = torch.from_numpy(z["concat"])
+    padded = torch.cat([c[:, :121], c.new_zeros(2, 7, 12, 20), c[:, 121:]], 1)
+    pd = padded.to(cuda_device, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    assert "tcgen05" in ops.deform_conv2d_variant([(5, 640, 7, 7)], ops.ConvSpec(640, 512, 3, 1, 1), torch.bfloat16, zero_offset=True)
+    x_reg, x_coeff = shift_candidates(net, pd, dev(z["boxes"], torch.float32, cuda_device), torch.from_numpy(z["pair"]).to(cuda_device))
+    assert x_reg.dtype == torch.float32
+    assert rel_err(x_reg.cpu().numpy(), z["x_reg"]) <= 1e-2, rel_err(x_reg.cpu().numpy(), z["x_reg"])
+    assert rel_err(x_coeff.cpu().numpy(), z["x_coeff"]) <= 1e-2, rel_err(x_coeff.cpu().numpy(), z["x_coeff"])
+
+
+def test_temporal_net_many_boxes_tcgen05_vs_cuda_cores(cuda_device):
+    """1500 boxes (73 500 GEMM rows: the paired 256-row plain-conv instantiation) — tcgen05 bf16 against the fp32
+    CUDA-core path of the same module, which the golden test above pins to the reference."""
+    from stmask_b200 import ops
+    _, net = _golden_temporal_net(cuda_device)
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    x = torch.relu(torch.randn((1500, 7, 7, 640), generator=g, device=cuda_device)).bfloat16().permute(0, 3, 1, 2)
+    x[:, 121:128] = 0
+    v = ops.deform_conv2d_variant([tuple(x.shape)], ops.ConvSpec(640, 512, 3, 1, 1), torch.bfloat16, zero_offset=True)
+    assert "plain=1" in v and "pair=1" in v and "rows=256" in v, v
+    ref_reg, ref_coeff = net(torch.cat([x[:, :121], x[:, 128:]], 1).float())            # fp32, reference channel layout
+    net16 = net.to(torch.bfloat16)
+    got_reg, got_coeff = net16(x)
+    # the fp32 run above used fp32 weights; the bf16 module rounds them — compare against fp32 math on the ROUNDED weights
+    ref_reg, ref_coeff = net16.float()(torch.cat([x[:, :121], x[:, 128:]], 1).float())
+    assert rel_err(got_reg.cpu().numpy(), ref_reg.cpu().numpy()) <= 1e-2
+    assert rel_err(got_coeff.cpu().numpy(), ref_coeff.cpu().numpy()) <= 1e-2
