@@ -303,6 +303,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sustained run, the per-layer table and the sweeps")
+    ap.add_argument("--multi-gpu-check", action="store_true", help="run the on-device multi-GPU correctness check even with --no-extras")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="frames per chunk of the streamed end-to-end path")
     ap.add_argument("--sustain-s", type=float, default=2.5)
     args = ap.parse_args()
@@ -446,6 +447,10 @@ def main():
                              "DRAM once, so the measured traffic is below the per-pair algorithmic bytes",
                      "peak_source": peaks["src"]}
 
+    # ---------------- on-device multi-GPU correctness: rank-sharded temporal fusion (halos over NCCL) == one GPU ----------
+    if world > 1 and hp_cfg.temporal_fusion and (not args.no_extras or args.multi_gpu_check):
+        extras["multi_gpu_check"] = multi_gpu_check(hp, inp, plan, rank, world, dev, n_clips, fpc)
+
     if not args.no_extras and rank == 0:
         extras["roofline_layers"] = layer_table(hp, inp, n_local, peaks, reps, args.backend)
         if world == 1:
@@ -542,6 +547,54 @@ def main():
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_check(hp, inp, plan, rank, world, dev, n_clips, fpc):
+    """Every rank computes the temporal-fusion concat of ITS frame pairs with the halos it received over NCCL (the
+    step's own code path); the features are all-gathered, rank 0 recomputes ALL pairs of all clips on one GPU without any
+    sharding and compares the gathered per-rank results with it bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from stmask_b200 import sharding
+    mine = hp(inp, plan, rank)["tf.concat"].contiguous(memory_format=torch.channels_last)
+    counts = [plan.local_frames(r) for r in range(world)]
+    pairs = [plan.local_pairs(r) for r in range(world)]
+
+    def gather(t, ns):
+        nhwc = t.permute(0, 2, 3, 1).contiguous()
+        bufs = [nhwc.new_empty((n,) + tuple(nhwc.shape[1:])) for n in ns]
+        dist.all_gather(bufs, nhwc) if len(set(ns)) == 1 else _all_gather_ragged(bufs, nhwc, rank, world)
+        return bufs
+    fpn, t2s, outs = gather(inp["tf.fpn"], counts), gather(inp["tf.t2s"], counts), gather(mine, pairs)
+    res = None
+    if rank == 0:
+        h, w, c = fpn[0].shape[1:]
+        full_f = fpn[0].new_empty((n_clips * fpc, h, w, c))
+        full_t = torch.empty_like(full_f)
+        for r in range(world):
+            for i, (clip, f) in enumerate(sharding.frame_order(plan, r)):
+                full_f[clip * fpc + f], full_t[clip * fpc + f] = fpn[r][i], t2s[r][i]
+        one = sharding.make_plan(n_clips, fpc, 1, "clip")
+        ref = hp._tf_pairs(full_f.permute(0, 3, 1, 2), full_t.permute(0, 3, 1, 2), one, 0, None).permute(0, 2, 3, 1)
+        pos = {cf: i for i, cf in enumerate(sharding.pair_frames(one, 0))}
+        bad = 0
+        for r in range(world):
+            idx = torch.tensor([pos[cf] for cf in sharding.pair_frames(plan, r)], device=dev, dtype=torch.long)
+            if idx.numel():
+                bad += int((ref.index_select(0, idx) != outs[r]).any(dim=(1, 2, 3)).sum())
+        res = {"tf_concat_bit_identical": bad == 0, "pairs_checked": int(sum(pairs)), "mismatching_pairs": bad,
+               "halos_per_rank": max(len(plan.recv_halos(r)) for r in range(world)), "sharding": plan.mode,
+               "how": "per-rank pair-indexed correlation+concat with NCCL halos vs. the unsharded single-GPU launch on all-gathered features"}
+    torch.cuda.synchronize()
+    return res
+
+
+def _all_gather_ragged(bufs, mine, rank, world):
+    import torch.distributed as dist
+    for r in range(world):
+        if r == rank:
+            bufs[r].copy_(mine)
+        dist.broadcast(bufs[r], src=r)
 
 
 def layer_table(hp, inp, n_local, peaks, reps, backend):

@@ -234,6 +234,16 @@ def pair_indices(plan: ShardPlan, rank: int) -> Tuple[List[int], List[int]]:
     return ref_idx, next_idx
 
 
+def pair_frames(plan: ShardPlan, rank: int) -> List[Tuple[int, int]]:
+    """(clip, frame t) of every (t-1, t) pair of this rank, in the order `pair_indices` / the correlation output use."""
+    return [(s.clip, f) for s in plan.segments[rank] for f in range(s.start, s.stop) if f > 0]
+
+
+def frame_order(plan: ShardPlan, rank: int) -> List[Tuple[int, int]]:
+    """(clip, frame) of every local frame of this rank, in local batch order."""
+    return [(s.clip, f) for s in plan.segments[rank] for f in range(s.start, s.stop)]
+
+
 _PAIR_INDEX_CACHE: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
 
 

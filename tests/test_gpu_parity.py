@@ -727,3 +727,46 @@ def test_temporal_net_many_boxes_tcgen05_vs_cuda_cores(cuda_device):
     ref_reg, ref_coeff = net16.float()(torch.cat([x[:, :121], x[:, 128:]], 1).float())
     assert rel_err(got_reg.cpu().numpy(), ref_reg.cpu().numpy()) <= 1e-2
     assert rel_err(got_coeff.cpu().numpy(), ref_coeff.cpu().numpy()) <= 1e-2
+
+
+# ------------------------------------------------------------------------------------------
+# CUDA-graph capture and replay of the whole step (the ABI promises: no allocation, no sync, stream-ordered)
+# ------------------------------------------------------------------------------------------
+def test_hot_path_step_is_cuda_graph_capturable(cuda_device):
+    from stmask_b200 import _lib, sharding
+    from stmask_b200.hotpath import HotPath, HotPathConfig
+    cfg = HotPathConfig(backbone="r50", fcb="ada", height=192, width=320)
+    hp = HotPath(cfg, cuda_device, seed=1)
+    plan = sharding.make_plan(2, 4, 1, "clip")
+    inp = hp.make_inputs(8, cuda_device, seed=5, on_device=True)
+    inp = {k: v.contiguous(memory_format=torch.channels_last) for k, v in inp.items()}
+    side = torch.cuda.Stream(cuda_device)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                            # warm-up: packs weights, fills the host-side caches
+        for _ in range(2):
+            eager = hp(inp, plan, 0)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    eager = {k: v.clone() for k, v in eager.items()}
+    graph = torch.cuda.CUDAGraph()
+    n0 = _lib.launch_count()
+    with torch.cuda.graph(graph):
+        captured = hp(inp, plan, 0)
+    n_kernels = _lib.launch_count() - n0
+    assert n_kernels >= 7 * 2 + 3 * 6 + 1                    # 7 DCN + 7 predictors, 3 x (5 offset kernels + 1 grouped FCB), 1 TF
+    graph.replay()
+    torch.cuda.synchronize()
+    for k, v in eager.items():
+        assert torch.equal(captured[k], v), k
+    # new data in the SAME input buffers, replay, compare with an eager run on that data
+    fresh = hp.make_inputs(8, cuda_device, seed=6, on_device=True)
+    for k in inp:
+        inp[k].copy_(fresh[k])
+    graph.replay()
+    torch.cuda.synchronize()
+    replayed = {k: v.clone() for k, v in captured.items()}
+    eager2 = hp(inp, plan, 0)
+    torch.cuda.synchronize()
+    for k, v in eager2.items():
+        assert torch.equal(replayed[k], v), k
+    assert not torch.equal(replayed["tf.concat"], eager["tf.concat"])

@@ -18,5 +18,6 @@ if d.get("roofline_sweep"):
 if d.get("e2e"):
     e = d["e2e"]
     print("e2e %.1f frames/s  ms/step %.2f  h2d %.2f GB d2h %.2f GB  ceiling %s frac %.2f  %s" % (e["value"], e["ms_per_step"], e["h2d_bytes_per_step"] / 1e9, e["d2h_bytes_per_step"] / 1e9, e.get("host_copy_ceiling"), e.get("frac_of_host_copy_ceiling", 0), e.get("host_placement")))
+print("multi_gpu_check", d.get("multi_gpu_check"))
 print("cpu_baseline", {k: v for k, v in (d.get("cpu_baseline") or {}).items() if k != "sample"})
 print("clocks", d.get("clocks"))
