@@ -88,7 +88,12 @@ enum {
   STM_DCN_OUT_F32 = 128,     /* y is float32 [.., out_c] (strides in float elements) whatever conv->dtype:
                                 the offset / mask-logit predictor of a DCN keeps its fp32 accumulators   */
   STM_DCN_HINT_DEEP_PIPE = 256, /* prefer more pipeline stages over L1 capacity                         */
-  STM_DCN_HINT_TWO_CTAS = 512   /* two 128-row CTAs with 8 producer warps each per SM                   */
+  STM_DCN_HINT_TWO_CTAS = 512,  /* two 128-row CTAs with 8 producer warps each per SM                   */
+  /* FCB, box-guided feature calibration (stm_deform_conv2d_fcb_fwd only): problem.offset is NOT the per-tap offset
+   * tensor but the regressed box deltas [batch, 4 = (t_x, t_y, t_w, t_h), out_h, out_w] (strides off_stride_*,
+   * dtype conv->offset_dtype); every tap's (dy, dx) is derived inside the sampling kernel. */
+  STM_DCN_FCB_ADA = 1024,       /* offsets = 1x1 conv_offset(deltas)            (Featurealign.py:20-25,44)   */
+  STM_DCN_FCB_ALI = 2048        /* offsets = closed form of the box transform   (Featurealign.py:46-69)      */
 };
 
 /* Parameters shared by every problem of one call (one weight tensor). */
@@ -138,6 +143,15 @@ size_t stm_deform_conv2d_workspace(const StmDcnConv* conv, const StmDcnProblem* 
 int stm_deform_conv2d_fwd(const StmDcnConv* conv, const StmDcnProblem* probs, int32_t n_probs,
                           const void* w_packed, const float* bias,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* FeatureAlign's `conv_adaption(x, offset(deltas))` with the offsets computed INSIDE the sampling kernel from the box
+ * deltas (conv->flags has STM_DCN_FCB_ADA or STM_DCN_FCB_ALI; see there): replaces stm_fcb_{ada,ali}_offsets + the
+ * offset tensors + stm_deform_conv2d_fwd for the hot path's shapes.  fcb_weight: float32 [deform_groups*2*kh*kw][4] (the
+ * 1x1 conv_offset weight) for ADA, NULL for ALI (deform_groups must be 1, odd kernel).  tcgen05 backend only:
+ * returns STM_ERR_UNSUPPORTED when the shape needs the CUDA-core kernel (callers then use the two-step form). */
+int stm_deform_conv2d_fcb_fwd(const StmDcnConv* conv, const StmDcnProblem* probs, int32_t n_probs,
+                              const void* w_packed, const float* bias, const float* fcb_weight,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* Which backend a call with these arguments would run: STM_BACKEND_SIMT / _TCGEN05,
  * or a negative StmStatus. */
@@ -226,6 +240,14 @@ int stm_correlation_fwd(const StmCorrDesc* desc, const void* x1, const void* x2,
                         const void* feat_a, const void* feat_b, void* out, void* stream);
 
 int stm_correlation_backend(const StmCorrDesc* desc);
+
+/* The same operator over n <= 8 feature maps in ONE launch (the FPN levels P3..P7 of the operator sweep): descs[i],
+ * x1s[i], x2s[i], outs[i] describe feature map i; C, patch, dilation, dtypes, flags and scale must be equal across
+ * them.  bf16 / tcgen05 only, no concat features, no pair indexing.  A desc with feat_c_offset > patch^2 (and no
+ * STM_CORR_COPY_FEATS) asks for zero-padded channels-last rows of feat_c_offset channels (128 for patch 11: 256-byte
+ * rows, written with 16-byte stores); channels [patch^2, feat_c_offset) are zeros. */
+int stm_correlation_multi_fwd(const StmCorrDesc* descs, const void* const* x1s, const void* const* x2s,
+                              void* const* outs, int32_t n, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* RoIAlign (average pooling) on an NHWC feature map                          */

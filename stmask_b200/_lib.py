@@ -19,6 +19,7 @@ BACKEND_NAMES = {BACKEND_AUTO: "auto", BACKEND_SIMT: "simt", BACKEND_TCGEN05: "t
 DCN_RELU, DCN_MASK_SIGMOID, DCN_ZERO_OFFSET = 1, 2, 4
 DCN_HINT_ROWS128, DCN_HINT_ROWS256, DCN_HINT_NO_PAIR = 16, 32, 64
 DCN_OUT_F32, DCN_HINT_DEEP_PIPE, DCN_HINT_TWO_CTAS = 128, 256, 512
+DCN_FCB_ADA, DCN_FCB_ALI = 1024, 2048
 CORR_LEAKY_RELU, CORR_RELU, CORR_COPY_FEATS = 1, 2, 4
 DCN_MAX_PROBLEMS = 8
 ABI_VERSION = 5
@@ -87,6 +88,8 @@ SIGNATURES = {
     "stm_deform_conv2d_workspace": (C.c_size_t, [C.POINTER(StmDcnConv), C.POINTER(StmDcnProblem), C.c_int32]),
     "stm_deform_conv2d_fwd": (C.c_int, [C.POINTER(StmDcnConv), C.POINTER(StmDcnProblem), C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "stm_deform_conv2d_fcb_fwd": (C.c_int, [C.POINTER(StmDcnConv), C.POINTER(StmDcnProblem), C.c_int32, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "stm_deform_conv2d_backend": (C.c_int, [C.POINTER(StmDcnConv), C.POINTER(StmDcnProblem), C.c_int32]),
     "stm_deform_conv2d_variant": (C.c_int, [C.POINTER(StmDcnConv), C.POINTER(StmDcnProblem), C.c_int32, C.c_char_p, C.c_size_t]),
     "stm_fcb_ali_offsets": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p, C.POINTER(C.c_int64),
@@ -97,6 +100,8 @@ SIGNATURES = {
     "stm_correlation_fwd": (C.c_int, [C.POINTER(StmCorrDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "stm_correlation_backend": (C.c_int, [C.POINTER(StmCorrDesc)]),
+    "stm_correlation_multi_fwd": (C.c_int, [C.POINTER(StmCorrDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "stm_roi_align_fwd": (C.c_int, [C.POINTER(StmRoiAlignDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "stm_pool_fc_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

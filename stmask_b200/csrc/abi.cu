@@ -95,8 +95,10 @@ static int validate_problems(const StmDcnConv* c, const StmDcnProblem* pr, int n
   return STM_OK;
 }
 
-static void fill_params(const StmDcnConv* c, const StmDcnProblem* pr, int n, const void* w, const float* bias, DcnParams* p) {
+static void fill_params(const StmDcnConv* c, const StmDcnProblem* pr, int n, const void* w, const float* bias, DcnParams* p,
+                        const float* fcb_w = nullptr) {
   memset(p, 0, sizeof(*p));
+  p->fcb_w = fcb_w;
   p->n_probs = 0;
   for (int i = 0; i < n; ++i) {
     const StmDcnProblem& q = pr[i];
@@ -115,7 +117,7 @@ static void fill_params(const StmDcnConv* c, const StmDcnProblem* pr, int n, con
   p->in_c = c->in_c; p->out_c = c->out_c; p->kh = c->kernel_h; p->kw = c->kernel_w;
   p->sh = c->stride_h; p->sw = c->stride_w; p->ph = c->pad_h; p->pw = c->pad_w; p->dh = c->dil_h; p->dw = c->dil_w;
   p->groups = c->groups; p->dg = c->deform_groups; p->flags = c->flags;
-  p->w = w; p->bias = bias;
+  p->w = w; p->bias = bias; p->fcb_w = fcb_w;
 }
 
 static int pick_dcn_backend(const StmDcnConv* c, const StmDcnProblem* pr, int n) {
@@ -235,6 +237,7 @@ int stm_deform_conv2d_fwd(const StmDcnConv* c, const StmDcnProblem* pr, int32_t 
   rc = validate_problems(c, pr, n);
   if (rc != STM_OK) return rc;
   STM_CHECK_ARG(w_packed != nullptr, "packed weight pointer is null");
+  STM_CHECK_ARG(!(c->flags & (STM_DCN_FCB_ADA | STM_DCN_FCB_ALI)), "STM_DCN_FCB_* flags belong to stm_deform_conv2d_fcb_fwd");
   const int be = pick_dcn_backend(c, pr, n);
   if (be < 0) return be;
   DcnParams p;
@@ -242,6 +245,33 @@ int stm_deform_conv2d_fwd(const StmDcnConv* c, const StmDcnProblem* pr, int32_t 
   if (p.n_probs == 0) return STM_OK;
   if (be == STM_BACKEND_TCGEN05) return launch_dcn_tc(c, p, workspace, ws_bytes, (cudaStream_t)stream);
   return launch_dcn_simt(p, c->dtype, c->offset_dtype, (cudaStream_t)stream);
+}
+
+int stm_deform_conv2d_fcb_fwd(const StmDcnConv* c, const StmDcnProblem* pr, int32_t n, const void* w_packed, const float* bias,
+                              const float* fcb_weight, void* workspace, size_t ws_bytes, void* stream) {
+  clear_error();
+  int rc = validate_conv(c);
+  if (rc != STM_OK) return rc;
+  rc = validate_problems(c, pr, n);
+  if (rc != STM_OK) return rc;
+  STM_CHECK_ARG(w_packed != nullptr, "packed weight pointer is null");
+  const int mode = c->flags & (STM_DCN_FCB_ADA | STM_DCN_FCB_ALI);
+  STM_CHECK_ARG(mode == STM_DCN_FCB_ADA || mode == STM_DCN_FCB_ALI, "flags must carry exactly one of STM_DCN_FCB_ADA / STM_DCN_FCB_ALI");
+  STM_CHECK_ARG(!(c->flags & STM_DCN_ZERO_OFFSET), "FCB offsets and STM_DCN_ZERO_OFFSET exclude each other");
+  STM_CHECK_ARG(c->stride_h == 1 && c->stride_w == 1, "FCB calibration convs have stride 1 (box deltas are per output pixel)");
+  if (mode == STM_DCN_FCB_ADA) STM_CHECK_ARG(fcb_weight != nullptr, "FCB(ada) needs the conv_offset weight");
+  if (mode == STM_DCN_FCB_ALI)
+    STM_CHECK_ARG(c->deform_groups == 1 && (c->kernel_h & 1) && (c->kernel_w & 1), "FCB(ali) offsets need deform_groups == 1 and an odd kernel");
+  for (int i = 0; i < n; ++i) STM_CHECK_ARG(pr[i].mask == nullptr, "FCB calibration is DCNv1 (no mask)");
+  const char* why = "";
+  if (c->backend == STM_BACKEND_SIMT || !dcn_tc_supported(c, pr, n, &why)) {
+    set_error("fused FCB offsets need the tcgen05 backend: %s", c->backend == STM_BACKEND_SIMT ? "SIMT backend requested" : why);
+    return STM_ERR_UNSUPPORTED;
+  }
+  DcnParams p;
+  fill_params(c, pr, n, w_packed, bias, &p, fcb_weight);
+  if (p.n_probs == 0) return STM_OK;
+  return launch_dcn_tc(c, p, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
 int stm_fcb_ali_offsets(const void* shape, const int64_t ss[4], int32_t sd, void* offset, const int64_t os[4], int32_t od,
@@ -289,6 +319,28 @@ int stm_correlation_fwd(const StmCorrDesc* d, const void* x1, const void* x2, co
   if (be == STM_BACKEND_TCGEN05) return launch_corr_tc(*d, x1, x2, fa, fb, out, (cudaStream_t)stream);
   if (d->x1_index != nullptr) { set_error("pair-indexed correlation needs the tcgen05 backend"); return STM_ERR_UNSUPPORTED; }
   return launch_corr_simt(*d, x1, x2, fa, fb, out, (cudaStream_t)stream);
+}
+
+int stm_correlation_multi_fwd(const StmCorrDesc* descs, const void* const* x1s, const void* const* x2s, void* const* outs,
+                              int32_t n, void* stream) {
+  clear_error();
+  STM_CHECK_ARG(descs && x1s && x2s && outs, "null pointer");
+  STM_CHECK_ARG(n >= 1 && n <= 8, "1..8 feature maps per launch (got %d)", n);
+  const StmCorrDesc& d0 = descs[0];
+  for (int i = 0; i < n; ++i) {
+    const StmCorrDesc& d = descs[i];
+    int rc = validate_corr(&d, x1s[i], x2s[i], nullptr, nullptr, outs[i]);
+    if (rc != STM_OK) return rc;
+    STM_CHECK_ARG(d.batch > 0, "feature map %d: empty batch", i);
+    STM_CHECK_ARG(d.c == d0.c && d.patch == d0.patch && d.dilation_patch == d0.dilation_patch && d.dtype == d0.dtype &&
+                  d.out_dtype == d0.out_dtype && d.flags == d0.flags && d.scale == d0.scale && d.leaky_slope == d0.leaky_slope &&
+                  d.feat_c_offset == d0.feat_c_offset,
+                  "feature map %d: C / patch / dilation / dtypes / flags / scale must match feature map 0", i);
+    STM_CHECK_ARG(!(d.flags & STM_CORR_COPY_FEATS) && d.x1_index == nullptr, "grouped launches take no concat features and no pair indices");
+    const char* why = "";
+    if (!corr_tc_supported(d, &why)) { set_error("grouped correlation needs the tcgen05 backend: %s (feature map %d)", why, i); return STM_ERR_UNSUPPORTED; }
+  }
+  return launch_corr_tc_multi(descs, x1s, x2s, nullptr, nullptr, outs, n, (cudaStream_t)stream);
 }
 
 int stm_roi_align_fwd(const StmRoiAlignDesc* d, const void* feat, const float* rois, void* out, void* stream) {

@@ -68,6 +68,7 @@ struct DcnParams {
   int32_t flags;
   const void* w;       // OHWI packed
   const float* bias;   // may be null
+  const float* fcb_w;  // FCB(ada): conv_offset weight [dg * 2 * kh * kw][4]; null otherwise
 };
 
 // ----------------------------------------------------------------------------------------
@@ -129,6 +130,8 @@ int launch_corr_simt(const StmCorrDesc& d, const void* x1, const void* x2, const
                      cudaStream_t stream);
 int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const void* fa, const void* fb, void* out,
                    cudaStream_t stream);
+int launch_corr_tc_multi(const StmCorrDesc* descs, const void* const* x1s, const void* const* x2s, const void* fa, const void* fb,
+                         void* const* outs, int n, cudaStream_t stream);
 bool corr_tc_supported(const StmCorrDesc& d, const char** why);
 int launch_pool_fc(const void* x, int dtype, int n, int hw, int c, int64_t x_stride_n, int64_t x_stride_p, const float* w,
                    const float* b, int out_features, float* y, cudaStream_t stream);

@@ -26,6 +26,7 @@
 // spatial_correlation_sampler and the elementwise tail of correlate()/CandidateShift
 // (reference track_to_segment_head.py:53-62, TF_utils.py:28-31).
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -42,12 +43,27 @@ constexpr int DRAIN_THREADS = DRAIN_WARPS * 32;
 constexpr int NUM_THREADS = 64 + DRAIN_THREADS + COPY_WARPS * 32;
 constexpr int MAX_P = 11;
 
+constexpr int MAX_LEVELS = 8;              // feature maps per grouped launch (the five FPN levels of the operator sweep)
+
+// One feature map of a grouped launch: every level has its own size, output and tensor maps; C, patch, dilation,
+// dtypes and post-ops are shared (args.d).  A single-map call is a grouped launch with one level.
+struct CorrLevel {
+  int32_t h, w, tile_begin, tiles_per_image;
+  void* out;
+  int64_t out_stride_n, out_stride_c, out_stride_h, out_stride_w;
+};
+
+struct CorrMaps {
+  CUtensorMap x1[MAX_LEVELS], x2[MAX_LEVELS], x1_alt;
+};
+
 struct CorrTcArgs {
   StmCorrDesc d;
+  CorrLevel lv[MAX_LEVELS];
+  int32_t n_levels, pad0_;
   const void* fa;
   const void* fb;
-  void* out;
-  int32_t n_tiles, tiles_per_image;
+  int32_t n_tiles, pad1_;
   int32_t th;              // tile height (tile width is the template parameter); th * TW <= 128
   int32_t rh, rw;          // region height / width in (sub-lattice) pixels
   int32_t n_half;          // N of each of the two MMAs (multiple of 16, <= 256)
@@ -76,11 +92,21 @@ struct TileCoord {
   int b, sy, sx, y0, x0;   // batch, sub-lattice phase, first pixel of the patch IN SUB-LATTICE coordinates
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const StmCorrDesc& d, int tile, int tiles_per_image, int th, int tw) {
+__device__ __forceinline__ int find_level(const CorrTcArgs& a, int tile) {
+  int l = 0;
+#pragma unroll 1
+  for (int i = 1; i < a.n_levels; ++i)
+    if (tile >= a.lv[i].tile_begin) l = i;
+  return l;
+}
+
+// `tile` is relative to the level's first tile
+__device__ __forceinline__ TileCoord decode_tile(const StmCorrDesc& dd, const CorrLevel& d, int tile, int th, int tw) {
   TileCoord t;
+  const int tiles_per_image = d.tiles_per_image;
   t.b = tile / tiles_per_image;
   int rem = tile - t.b * tiles_per_image;
-  const int dl = d.dilation_patch;
+  const int dl = dd.dilation_patch;
   t.sy = t.sx = t.y0 = t.x0 = 0;
   for (int sy = 0; sy < dl; ++sy)
     for (int sx = 0; sx < dl; ++sx) {
@@ -125,8 +151,7 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
 // POST: 0 = scale only, 1 = leaky-ReLU, 2 = ReLU (ReLU after leaky-ReLU is ReLU)
 template <typename OT, int TW, int POST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUtensorMap tmap_x1,
-               const __grid_constant__ CUtensorMap tmap_x2, const __grid_constant__ CUtensorMap tmap_x1_alt) {
+corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CorrMaps maps) {
   constexpr int MAX_RW = TW + MAX_P - 1;          // <= 32: one tcgen05.ld.x32 covers a region row
   static_assert(MAX_RW <= 32, "tile too wide");
   extern __shared__ uint8_t smem_raw[];
@@ -145,8 +170,8 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
   const int th = a.th, npix = th * TW;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tmap_x1);
-    prefetch_tensormap(&tmap_x2);
+    prefetch_tensormap(&maps.x1[0]);
+    prefetch_tensormap(&maps.x2[0]);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -186,27 +211,30 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
       uint32_t phase = 0;
       const uint32_t bytes = (uint32_t)((npix + a.rh * a.rw) * 128);
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
-        const TileCoord t = decode_tile(d, tile, a.tiles_per_image, th, TW);
+        const int lvl = find_level(a, tile);
+        const TileCoord t = decode_tile(d, a.lv[lvl], tile - a.lv[lvl].tile_begin, th, TW);
         const int fy = t.sy + dl * t.y0, fx = t.sx + dl * t.x0;           // full-resolution coords of the patch origin
         const PairFrames pf = pair_frames(d, t.b);
-        const CUtensorMap* m1 = pf.alt ? &tmap_x1_alt : &tmap_x1;
+        const CUtensorMap* m1 = pf.alt ? &maps.x1_alt : &maps.x1[lvl];
+        const CUtensorMap* m2 = &maps.x2[lvl];
         for (int c = 0; c < a.chunks; ++c) {
           mbar_wait_relaxed(&empty_bar[s], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], bytes);
           uint8_t* st = smem + s * L.stage_bytes;
           tma_load_4d(st, m1, &full_bar[s], c * 64, fx, fy, pf.b1);
-          tma_load_4d(st + L.a_bytes, &tmap_x2, &full_bar[s], c * 64, fx - r * dl, fy - r * dl, pf.b2);
+          tma_load_4d(st + L.a_bytes, m2, &full_bar[s], c * 64, fx - r * dl, fy - r * dl, pf.b2);
           if (a.l2_prefetch) {
             // the smem ring holds only STAGES chunks: pull the chunk that will be loaded STAGES steps from now into
             // L2 already, so that load does not pay DRAM latency on the MMA's critical path
             int pc = c + STAGES, ptile = tile;
             if (pc >= a.chunks) { pc -= a.chunks; ptile += gridDim.x; }
             if (ptile < a.n_tiles) {
-              const TileCoord n = ptile == tile ? t : decode_tile(d, ptile, a.tiles_per_image, th, TW);
+              const int nl = ptile == tile ? lvl : find_level(a, ptile);
+              const TileCoord n = ptile == tile ? t : decode_tile(d, a.lv[nl], ptile - a.lv[nl].tile_begin, th, TW);
               const int ny = n.sy + dl * n.y0, nx = n.sx + dl * n.x0;
               const PairFrames nf = ptile == tile ? pf : pair_frames(d, n.b);
-              tma_prefetch_4d(nf.alt ? &tmap_x1_alt : &tmap_x1, pc * 64, nx, ny, nf.b1);
-              tma_prefetch_4d(&tmap_x2, pc * 64, nx - r * dl, ny - r * dl, nf.b2);
+              tma_prefetch_4d(nf.alt ? &maps.x1_alt : &maps.x1[nl], pc * 64, nx, ny, nf.b1);
+              tma_prefetch_4d(&maps.x2[nl], pc * 64, nx - r * dl, ny - r * dl, nf.b2);
             }
           }
           if (c == 0) STM_TRACE(k, 0);
@@ -258,12 +286,13 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
     constexpr bool relu = POST == 2;
     const bool copy_feats = (d.flags & STM_CORR_COPY_FEATS) != 0;
     const int fc = d.feat_c, foff = a.feat_off;
-    OT* out = reinterpret_cast<OT*>(a.out);
-    const bool nhwc = d.out_stride_c == 1;
     int k = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles && copy_feats; tile += gridDim.x, ++k) {
-      const TileCoord t = decode_tile(d, tile, a.tiles_per_image, th, TW);
-      const int64_t obase = t.b * d.out_stride_n;
+      const CorrLevel& lv = a.lv[find_level(a, tile)];
+      OT* out = reinterpret_cast<OT*>(lv.out);
+      const bool nhwc = lv.out_stride_c == 1;
+      const TileCoord t = decode_tile(d, lv, tile - lv.tile_begin, th, TW);
+      const int64_t obase = t.b * lv.out_stride_n;
       const PairFrames pf = pair_frames(d, t.b);
       if (et == 0) STM_TRACE(k, 4);
       // ---- phase 0: concat copy of the two feature maps behind the correlation channels.  It does not
@@ -280,7 +309,7 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
             const int m = item & 1, seg = (item >> 1) & 1, ty = item >> 2;
             const int y = t.sy + dl * (t.y0 + ty);
             const int x = t.sx + dl * (t.x0 + seg * SEG);                       // first pixel of the segment
-            int nv = y < d.h ? (d.w - x + dl - 1) / dl : 0;                     // valid pixels in it
+            int nv = y < lv.h ? (lv.w - x + dl - 1) / dl : 0;                   // valid pixels in it
             nv = nv < 0 ? 0 : (nv > SEG ? SEG : nv);
             const bool alt = m == 0 && pf.alt;
             const int64_t fsw_ = m ? d.feat_b_stride_w : (alt ? d.feat_a_alt_stride_w : d.feat_a_stride_w);
@@ -289,8 +318,8 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
                 m ? reinterpret_cast<const __nv_bfloat16*>(a.fb) + pf.b2 * d.feat_b_stride_n + y * d.feat_b_stride_h + x * d.feat_b_stride_w
                   : (alt ? reinterpret_cast<const __nv_bfloat16*>(d.feat_a_alt) + pf.b1 * d.feat_a_alt_stride_n + y * d.feat_a_alt_stride_h + x * d.feat_a_alt_stride_w
                          : reinterpret_cast<const __nv_bfloat16*>(a.fa) + pf.b1 * d.feat_a_stride_n + y * d.feat_a_stride_h + x * d.feat_a_stride_w);
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.out) + obase + y * d.out_stride_h + x * d.out_stride_w + foff + m * fc;
-            const int64_t osw = d.out_stride_w * dl;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(lv.out) + obase + y * lv.out_stride_h + x * lv.out_stride_w + foff + m * fc;
+            const int64_t osw = lv.out_stride_w * dl;
             for (int ch = lane; ch < cpr; ch += 32) {
               uint4 v[SEG];
 #pragma unroll
@@ -319,18 +348,18 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
           for (int pix = p_begin; pix < npix; pix += p_step) {
             const int ty = pix / TW, tx = pix - ty * TW;
             const int y = t.sy + dl * (t.y0 + ty), x = t.sx + dl * (t.x0 + tx);
-            if (y >= d.h || x >= d.w) continue;
-            OT* op = out + obase + y * d.out_stride_h + x * d.out_stride_w;
+            if (y >= lv.h || x >= lv.w) continue;
+            OT* op = out + obase + y * lv.out_stride_h + x * lv.out_stride_w;
             const void* fa_ = pf.alt ? d.feat_a_alt : a.fa;
             const int64_t ia = pf.alt ? pf.b1 * d.feat_a_alt_stride_n + y * d.feat_a_alt_stride_h + x * d.feat_a_alt_stride_w
                                       : pf.b1 * d.feat_a_stride_n + y * d.feat_a_stride_h + x * d.feat_a_stride_w;
             const int64_t ib = pf.b2 * d.feat_b_stride_n + y * d.feat_b_stride_h + x * d.feat_b_stride_w;
 #pragma unroll 4
             for (int c = c_begin; c < fc; c += c_step) {
-              op[(int64_t)(foff + c) * d.out_stride_c] = from_f32<OT>(feat(fa_, ia + c));
-              op[(int64_t)(foff + fc + c) * d.out_stride_c] = from_f32<OT>(feat(a.fb, ib + c));
+              op[(int64_t)(foff + c) * lv.out_stride_c] = from_f32<OT>(feat(fa_, ia + c));
+              op[(int64_t)(foff + fc + c) * lv.out_stride_c] = from_f32<OT>(feat(a.fb, ib + c));
             }
-            for (int c = PP + c_begin; c < foff; c += c_step) op[(int64_t)c * d.out_stride_c] = from_f32<OT>(0.f);
+            for (int c = PP + c_begin; c < foff; c += c_step) op[(int64_t)c * lv.out_stride_c] = from_f32<OT>(0.f);
           }
         }
       }
@@ -352,13 +381,14 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
     const int S = a.stage_stride;
     const float scale = d.scale, slope = d.leaky_slope;
     const int foff = a.feat_off;
-    OT* out = reinterpret_cast<OT*>(a.out);
-    const bool nhwc = d.out_stride_c == 1;
     uint32_t tphase = 0;
     int k = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++k) {
-      const TileCoord t = decode_tile(d, tile, a.tiles_per_image, th, TW);
-      const int64_t obase = t.b * d.out_stride_n;
+      const CorrLevel& lv = a.lv[find_level(a, tile)];
+      OT* out = reinterpret_cast<OT*>(lv.out);
+      const bool nhwc = lv.out_stride_c == 1;
+      const TileCoord t = decode_tile(d, lv, tile - lv.tile_begin, th, TW);
+      const int64_t obase = t.b * lv.out_stride_n;
       mbar_wait(tmem_full, tphase);
       tcgen05_fence_after();
       if (et == 0) STM_TRACE(k, 6);
@@ -390,15 +420,15 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
       if (a.fast) {
         // channels [0, feat_off) of every pixel: one half-warp per pixel, 16-byte chunks
         const int cpp = foff >> 3;
-        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(a.out) + obase;
+        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(lv.out) + obase;
         const int l16 = et & 15;
 #pragma unroll 2
         for (int pix = et >> 4; pix < npix; pix += EPI_THREADS / 16) {
           const int ty = pix / TW, tx = pix - ty * TW;
           const int y = t.sy + dl * (t.y0 + ty), x = t.sx + dl * (t.x0 + tx);
-          if (y < d.h && x < d.w) {
+          if (y < lv.h && x < lv.w) {
             const uint2* sp = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(staging) + pix * S);
-            uint4* op = reinterpret_cast<uint4*>(ob + y * d.out_stride_h + x * d.out_stride_w);
+            uint4* op = reinterpret_cast<uint4*>(ob + y * lv.out_stride_h + x * lv.out_stride_w);
             for (int ch = l16; ch < cpp; ch += 16) {
               const uint2 lo = sp[2 * ch], hi = sp[2 * ch + 1];
               op[ch] = make_uint4(lo.x, lo.y, hi.x, hi.y);
@@ -411,8 +441,8 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
         for (int pix = ew; pix < npix; pix += EPI_WARPS) {
           const int ty = pix / TW, tx = pix - ty * TW;
           const int y = t.sy + dl * (t.y0 + ty), x = t.sx + dl * (t.x0 + tx);
-          if (y < d.h && x < d.w) {
-            OT* orow = out + obase + y * d.out_stride_h + x * d.out_stride_w;
+          if (y < lv.h && x < lv.w) {
+            OT* orow = out + obase + y * lv.out_stride_h + x * lv.out_stride_w;
             const OT* srow = staging + pix * S;
             for (int k = lane; k < PP; k += 32) orow[k] = srow[k];
           }
@@ -423,11 +453,11 @@ corr_tc_kernel(const __grid_constant__ CorrTcArgs a, const __grid_constant__ CUt
         const int pix = et & 127;
         const int ty = pix / TW, tx = pix - ty * TW;
         const int y = t.sy + dl * (t.y0 + ty), x = t.sx + dl * (t.x0 + tx);
-        if (pix < npix && y < d.h && x < d.w) {
-          OT* op = out + obase + y * d.out_stride_h + x * d.out_stride_w;
+        if (pix < npix && y < lv.h && x < lv.w) {
+          OT* op = out + obase + y * lv.out_stride_h + x * lv.out_stride_w;
           const OT* srow = staging + pix * S;
 #pragma unroll 8
-          for (int k = et >> 7; k < PP; k += EPI_THREADS / 128) op[(int64_t)k * d.out_stride_c] = srow[k];
+          for (int k = et >> 7; k < PP; k += EPI_THREADS / 128) op[(int64_t)k * lv.out_stride_c] = srow[k];
         }
       }
       named_barrier_sync(2, EPI_THREADS);              // staging free for the next tile
@@ -463,12 +493,11 @@ int encode_nhwc_map(CUtensorMap* m, const void* ptr, int c, int w, int h, int b,
 SmemAttrCache g_corr_smem_attr[12];    // one per instantiation (out dtype x tile width x post-op)
 
 template <typename OT, int TW, int POST>
-int launch_t(const CorrTcArgs& args, const CUtensorMap& m1, const CUtensorMap& m2, const CUtensorMap& m1a, int grid, int smem_bytes,
-             cudaStream_t stream) {
+int launch_t(const CorrTcArgs& args, const CorrMaps& maps, int grid, int smem_bytes, cudaStream_t stream) {
   constexpr int slot = (sizeof(OT) == 4 ? 6 : 0) + (TW == 20 ? 3 : 0) + POST;
   const int rc = ensure_dynamic_smem(corr_tc_kernel<OT, TW, POST>, smem_bytes, g_corr_smem_attr[slot]);
   if (rc != STM_OK) return rc;
-  corr_tc_kernel<OT, TW, POST><<<grid, NUM_THREADS, smem_bytes, stream>>>(args, m1, m2, m1a);
+  corr_tc_kernel<OT, TW, POST><<<grid, NUM_THREADS, smem_bytes, stream>>>(args, maps);
   count_launch();
   STM_CUDA_OK(cudaGetLastError());
   return STM_OK;
@@ -505,20 +534,27 @@ bool corr_tc_supported(const StmCorrDesc& d, const char** why) {
   return true;
 }
 
-int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const void* fa, const void* fb, void* out,
-                   cudaStream_t stream) {
-  if (((uintptr_t)x1 & 15) || ((uintptr_t)x2 & 15)) {
-    // descriptors need 16-byte aligned bases; rare (sliced tensors) -> CUDA-core kernel, which knows nothing
-    // about pair indexing
-    if (d.x1_index != nullptr) {
-      set_error("pair-indexed correlation needs 16-byte aligned x1 / x2 (tcgen05 backend only)");
-      return STM_ERR_UNSUPPORTED;
+// One launch over n feature maps (levels) that share C, patch, dilation, dtypes and post-ops: descs[i] carries level
+// i's size, strides and (for i == 0 only) the concat / pair-indexing fields.
+int launch_corr_tc_multi(const StmCorrDesc* descs, const void* const* x1s, const void* const* x2s, const void* fa, const void* fb,
+                         void* const* outs, int n, cudaStream_t stream) {
+  const StmCorrDesc& d = descs[0];
+  if (n < 1 || n > MAX_LEVELS) { set_error("1..%d feature maps per launch, got %d", MAX_LEVELS, n); return STM_ERR_INVALID_ARGUMENT; }
+  for (int i = 0; i < n; ++i) {
+    if (((uintptr_t)x1s[i] & 15) || ((uintptr_t)x2s[i] & 15)) {
+      // descriptors need 16-byte aligned bases; rare (sliced tensors) -> CUDA-core kernel, which knows nothing
+      // about pair indexing or grouped launches
+      if (d.x1_index != nullptr || n > 1) {
+        set_error("pair-indexed / grouped correlation needs 16-byte aligned x1 / x2 (tcgen05 backend only)");
+        return STM_ERR_UNSUPPORTED;
+      }
+      return launch_corr_simt(d, x1s[0], x2s[0], fa, fb, outs[0], stream);
     }
-    return launch_corr_simt(d, x1, x2, fa, fb, out, stream);
   }
   CorrTcArgs args;
+  memset(&args, 0, sizeof(args));
   args.d = d;
-  args.fa = fa; args.fb = fb; args.out = out;
+  args.fa = fa; args.fb = fb;
   args.trace = nullptr;
   args.l2_prefetch = 1;
 #ifdef STM_DCN_EXPERIMENTS   // profiling builds only (tools/corr_trace.py); the product library has no environment knobs
@@ -529,7 +565,8 @@ int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const v
   // tile shape: fewest tiles wins (6x20 tiles a 24x40 map exactly: 8 tiles instead of 9); ties -> 8x16
   int tw = 16, th = 8;
   {
-    const int t816 = tiles_per_image(d, 8, 16), t620 = tiles_per_image(d, 6, 20);
+    int t816 = 0, t620 = 0;
+    for (int i = 0; i < n; ++i) { t816 += tiles_per_image(descs[i], 8, 16) * descs[i].batch; t620 += tiles_per_image(descs[i], 6, 20) * descs[i].batch; }
     if (t620 < t816) { tw = 20; th = 6; }
   }
   args.th = th;
@@ -544,20 +581,40 @@ int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const v
   while (cols < need_cols) cols <<= 1;
   if (cols > 512) { set_error("tcgen05 correlation: region of %d pixels does not fit TMEM", n_region); return STM_ERR_UNSUPPORTED; }
   args.tmem_cols = cols;
-  args.tiles_per_image = tiles_per_image(d, th, tw);
-  args.n_tiles = args.tiles_per_image * d.batch;
+  args.n_levels = n;
+  args.n_tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    const StmCorrDesc& q = descs[i];
+    CorrLevel& lv = args.lv[i];
+    lv.h = q.h; lv.w = q.w;
+    lv.tile_begin = args.n_tiles;
+    lv.tiles_per_image = tiles_per_image(q, th, tw);
+    lv.out = outs[i];
+    lv.out_stride_n = q.out_stride_n; lv.out_stride_c = q.out_stride_c; lv.out_stride_h = q.out_stride_h; lv.out_stride_w = q.out_stride_w;
+    args.n_tiles += lv.tiles_per_image * q.batch;
+  }
   if (args.n_tiles == 0) return STM_OK;
   const int oes = d.out_dtype == STM_F32 ? 4 : 2;
   const bool copy = (d.flags & STM_CORR_COPY_FEATS) != 0;
-  args.feat_off = (copy && d.feat_c_offset > 0) ? d.feat_c_offset : P * P;
+  // first channel behind the P*P correlation channels: the concat's feature block, or (without a concat) the end of a
+  // zero-padded cost-volume row — feat_c_offset = 128 for P = 11 gives 256-byte channels-last rows
+  args.feat_off = d.feat_c_offset > P * P ? d.feat_c_offset : P * P;
   // aligned channels-last epilogue: bf16 everywhere, every pixel row / feature block / feature row 16-byte aligned
-  args.fast = copy && d.out_stride_c == 1 && d.out_dtype == STM_BF16 && d.feat_dtype == STM_BF16 &&
-              (d.feat_c & 7) == 0 && (args.feat_off & 7) == 0 &&
-              ((d.out_stride_n | d.out_stride_h | d.out_stride_w) & 7) == 0 &&
-              (((d.feat_a_stride_n | d.feat_a_stride_h | d.feat_a_stride_w | d.feat_b_stride_n | d.feat_b_stride_h | d.feat_b_stride_w) & 7) == 0) &&
-              ((((uintptr_t)fa | (uintptr_t)fb | (uintptr_t)out) & 15) == 0) &&
-              (!(d.x1_index != nullptr && d.alt_frames > 0) ||
-               ((((uintptr_t)d.feat_a_alt) & 15) == 0 && ((d.feat_a_alt_stride_n | d.feat_a_alt_stride_h | d.feat_a_alt_stride_w) & 7) == 0));
+  bool fast = d.out_dtype == STM_BF16 && (args.feat_off & 7) == 0 && (copy || args.feat_off > P * P);
+  for (int i = 0; i < n && fast; ++i)
+    fast = descs[i].out_stride_c == 1 && ((descs[i].out_stride_n | descs[i].out_stride_h | descs[i].out_stride_w) & 7) == 0 &&
+           (((uintptr_t)outs[i]) & 15) == 0;
+  if (copy)
+    fast = fast && d.feat_dtype == STM_BF16 && (d.feat_c & 7) == 0 &&
+           (((d.feat_a_stride_n | d.feat_a_stride_h | d.feat_a_stride_w | d.feat_b_stride_n | d.feat_b_stride_h | d.feat_b_stride_w) & 7) == 0) &&
+           ((((uintptr_t)fa | (uintptr_t)fb) & 15) == 0) &&
+           (!(d.x1_index != nullptr && d.alt_frames > 0) ||
+            ((((uintptr_t)d.feat_a_alt) & 15) == 0 && ((d.feat_a_alt_stride_n | d.feat_a_alt_stride_h | d.feat_a_alt_stride_w) & 7) == 0));
+  args.fast = fast ? 1 : 0;
+  if (!fast && !copy && args.feat_off > P * P) {
+    set_error("a zero-padded cost volume (feat_c_offset > patch^2 without COPY_FEATS) needs channels-last bf16 output with 16-byte aligned rows");
+    return STM_ERR_UNSUPPORTED;
+  }
   // staging row stride (elements).  fast: feat_off elements + 4 (rows stay 8-byte aligned for LDS.64, and the
   // 2-word skew spreads the band scatter over the banks); generic: an odd number of 32-bit words per pixel
   args.stage_stride = args.fast ? args.feat_off + 4 : (oes == 4 ? (P * P + 2) : ((P * P + 3) & ~1));
@@ -566,31 +623,35 @@ int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const v
 
   // frame counts of the tensors behind the maps (pair indexing addresses frames, not pairs)
   const bool indexed = d.x1_index != nullptr;
-  const int nb1 = indexed ? d.x1_frames : d.batch, nb2 = indexed ? d.x2_frames : d.batch;
-  CUtensorMap m1, m2, m1a;
-  int rc = encode_nhwc_map(&m1, x1, d.c, d.w, d.h, nb1, d.x1_stride_w, d.x1_stride_h, nb1 > 1 ? d.x1_stride_n : (int64_t)d.h * d.x1_stride_h,
-                           tw, th, dl);
-  if (rc != STM_OK) return rc;
-  rc = encode_nhwc_map(&m2, x2, d.c, d.w, d.h, nb2, d.x2_stride_w, d.x2_stride_h, nb2 > 1 ? d.x2_stride_n : (int64_t)d.h * d.x2_stride_h,
-                       args.rw, args.rh, dl);
-  if (rc != STM_OK) return rc;
-  m1a = m1;
+  CorrMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int i = 0; i < n; ++i) {
+    const StmCorrDesc& q = descs[i];
+    const int nb1 = indexed ? q.x1_frames : q.batch, nb2 = indexed ? q.x2_frames : q.batch;
+    int rc = encode_nhwc_map(&maps.x1[i], x1s[i], q.c, q.w, q.h, nb1, q.x1_stride_w, q.x1_stride_h,
+                             nb1 > 1 ? q.x1_stride_n : (int64_t)q.h * q.x1_stride_h, tw, th, dl);
+    if (rc != STM_OK) return rc;
+    rc = encode_nhwc_map(&maps.x2[i], x2s[i], q.c, q.w, q.h, nb2, q.x2_stride_w, q.x2_stride_h,
+                         nb2 > 1 ? q.x2_stride_n : (int64_t)q.h * q.x2_stride_h, args.rw, args.rh, dl);
+    if (rc != STM_OK) return rc;
+  }
+  maps.x1_alt = maps.x1[0];
   if (indexed && d.alt_frames > 0) {
     if (((uintptr_t)d.x1_alt & 15) || ((d.x1_alt_stride_n | d.x1_alt_stride_h | d.x1_alt_stride_w) & 7)) {
       set_error("x1_alt must be 16-byte aligned with strides that are multiples of 8 elements");
       return STM_ERR_INVALID_ARGUMENT;
     }
-    rc = encode_nhwc_map(&m1a, d.x1_alt, d.c, d.w, d.h, d.alt_frames, d.x1_alt_stride_w, d.x1_alt_stride_h,
-                         d.alt_frames > 1 ? d.x1_alt_stride_n : (int64_t)d.h * d.x1_alt_stride_h, tw, th, dl);
+    const int rc = encode_nhwc_map(&maps.x1_alt, d.x1_alt, d.c, d.w, d.h, d.alt_frames, d.x1_alt_stride_w, d.x1_alt_stride_h,
+                                   d.alt_frames > 1 ? d.x1_alt_stride_n : (int64_t)d.h * d.x1_alt_stride_h, tw, th, dl);
     if (rc != STM_OK) return rc;
   }
   const int grid = args.n_tiles < device_sm_count() ? args.n_tiles : device_sm_count();
   const int post = (d.flags & STM_CORR_RELU) ? 2 : ((d.flags & STM_CORR_LEAKY_RELU) ? 1 : 0);
 #define STM_CORR_LAUNCH(OT_, TW_)                                                                     \
   do {                                                                                                \
-    if (post == 2) return launch_t<OT_, TW_, 2>(args, m1, m2, m1a, grid, L.total, stream);                 \
-    if (post == 1) return launch_t<OT_, TW_, 1>(args, m1, m2, m1a, grid, L.total, stream);                 \
-    return launch_t<OT_, TW_, 0>(args, m1, m2, m1a, grid, L.total, stream);                                \
+    if (post == 2) return launch_t<OT_, TW_, 2>(args, maps, grid, L.total, stream);                        \
+    if (post == 1) return launch_t<OT_, TW_, 1>(args, maps, grid, L.total, stream);                        \
+    return launch_t<OT_, TW_, 0>(args, maps, grid, L.total, stream);                                       \
   } while (0)
   if (tw == 20) {
     if (d.out_dtype == STM_F32) STM_CORR_LAUNCH(float, 20);
@@ -599,6 +660,11 @@ int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const v
   if (d.out_dtype == STM_F32) STM_CORR_LAUNCH(float, 16);
   STM_CORR_LAUNCH(__nv_bfloat16, 16);
 #undef STM_CORR_LAUNCH
+}
+
+int launch_corr_tc(const StmCorrDesc& d, const void* x1, const void* x2, const void* fa, const void* fb, void* out,
+                   cudaStream_t stream) {
+  return launch_corr_tc_multi(&d, &x1, &x2, fa, fb, &out, 1, stream);
 }
 
 }  // namespace stm

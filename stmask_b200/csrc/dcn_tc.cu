@@ -72,14 +72,16 @@ struct TcArgs {
 template <int M_TILES>
 struct SmemLayout {
   static constexpr int ROWS = TILE_M * M_TILES;
-  int stage_bytes, meta_p, meta_w, bars, total;
-  // pair: each CTA of a cta_group::2 pair holds only its half of the N tile's weight rows
-  __host__ __device__ SmemLayout(int block_n, int stages, bool pair) {
+  int stage_bytes, meta_p, meta_w, bars, fcb_w, total;
+  // pair: each CTA of a cta_group::2 pair holds only its half of the N tile's weight rows;
+  // fcb_floats: FCB(ada) conv_offset weights [dg * 2K][4] kept in shared memory
+  __host__ __device__ SmemLayout(int block_n, int stages, bool pair, int fcb_floats = 0) {
     stage_bytes = M_TILES * A_TILE_BYTES + (pair ? block_n / 2 : block_n) * 128;
     int off = stages * stage_bytes;
     meta_p = off; off += META_BUFS * ROWS * 32;    // four 64-bit corner pointers per row
     meta_w = off; off += META_BUFS * ROWS * 8;     // four bf16 corner weights per row
     bars = off;   off += (2 * MAX_STAGES + 2) * 8;
+    fcb_w = off;  off += (fcb_floats * 4 + 15) & ~15;
     total = off + 1024;   // slack for manual 1024-byte alignment of the base
   }
 };
@@ -119,9 +121,16 @@ __device__ __forceinline__ uint64_t add_wide(uint32_t lo, uint32_t hi, uint32_t 
 // load and a store (no blend) and the metadata is one pointer per row.  This is the regular convolution that
 // predicts a DCN's offsets / mask logits (backbone.py:24-26) and the TemporalNet convs
 // (track_to_segment_head.py:14-16) on the same tcgen05 main loop.
-template <int M_TILES, int PW, int D, bool PAIR, bool PLAIN>
+//
+// MODE 2 (FCB, box-guided offsets): `offset` is not the per-tap offset tensor but the four regressed box deltas
+// (t_x, t_y, t_w, t_h) per pixel; the producers derive every tap's (dy, dx) themselves while they compute the
+// sampling metadata — FCB(ada): the 1x1 `conv_offset` (8 FMAs per tap, weights in shared memory), FCB(ali): the closed
+// form of Featurealign.py:46-69.  The 30-channel offset tensors and the kernels that wrote them disappear.
+template <int M_TILES, int PW, int D, bool PAIR, int MODE>
 __global__ void __launch_bounds__(PW * 32 + 64, (M_TILES == 1 && PW == 8) ? 2 : 1)
 dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensorMap tmap_w) {
+  constexpr bool PLAIN = MODE == 1;
+  constexpr bool FCB = MODE == 2;
   constexpr int ROWS = TILE_M * M_TILES;
   constexpr int PT = PW * 32;                           // producer threads
   constexpr int ROWS_PER_PASS = PW * 4;                 // rows covered by one sweep of the producer warps
@@ -132,7 +141,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   static_assert(D >= 1 && D <= TPK && TPK % D == 0, "gather look-ahead must divide the tasks per K block");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SmemLayout<M_TILES> L(a.block_n, a.stages, PAIR);
+  const SmemLayout<M_TILES> L(a.block_n, a.stages, PAIR, FCB ? a.p.dg * 2 * a.p.kh * a.p.kw * 4 : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* accum_bar = empty_bar + MAX_STAGES;
@@ -166,6 +175,10 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
+  if (FCB && (p.flags & STM_DCN_FCB_ADA) && warp < PW) {
+    float* fw = reinterpret_cast<float*>(smem + L.fcb_w);
+    for (int i = tid; i < p.dg * 2 * p.kh * p.kw * 4; i += PW * 32) fw[i] = __ldg(p.fcb_w + i);
+  }
   if (warp == PW + 1) {
     if (PAIR) { tmem_alloc_pair(tmem_slot, (uint32_t)a.tmem_cols); tmem_relinquish_pair(); }
     else { tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols); tmem_relinquish(); }
@@ -194,7 +207,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
 
     // ---- sample metadata: thread -> (row, CPT of its 4 corners) ----
     const int mrow = tid % ROWS, cg = tid / ROWS;
-    const bool has_off = !PLAIN && pr.offset != nullptr, has_mask = !PLAIN && pr.mask != nullptr;
+    const bool has_off = !PLAIN && !FCB && pr.offset != nullptr, has_mask = !PLAIN && !FCB && pr.mask != nullptr;
     const bool off_bf16 = (p.flags & FLAG_OFFSETS_BF16) != 0;      // internal flag: offsets/masks stored as bf16
     const bool mask_sig = has_mask && (p.flags & STM_DCN_MASK_SIGMOID);
     int hb = 0, wb = 0;                     // top-left of the un-deformed receptive field
@@ -219,9 +232,22 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     const uint64_t zero_page = reinterpret_cast<uint64_t>(g_zero_page);
 
     // raw (dy, dx, mask) of this thread's row for iteration `it`; issued one iteration ahead of its use
-    auto load_raw = [&](int it_, float& oy, float& ox, float& mk) {
-      oy = 0.f; ox = 0.f; mk = 1.f;
+    // (FCB: the four box deltas (t_x, t_y, t_w, t_h) of the row instead — the same for every tap, an L1 hit after the first)
+    const bool fcb_ada = FCB && (p.flags & STM_DCN_FCB_ADA) != 0;
+    auto load_raw = [&](int it_, float& oy, float& ox, float& mk, float& r3) {
+      oy = 0.f; ox = 0.f; mk = FCB ? 0.f : 1.f; r3 = 0.f;
       if (PLAIN || !rvalid || it_ >= n_iter) return;
+      if (FCB) {
+        if (off_bf16) {
+          const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(pr.offset) + off_base;
+          oy = __bfloat162float(__ldg(bp)); ox = __bfloat162float(__ldg(bp + pr.off_sc));
+          mk = __bfloat162float(__ldg(bp + 2 * pr.off_sc)); r3 = __bfloat162float(__ldg(bp + 3 * pr.off_sc));
+        } else {
+          const float* bp = reinterpret_cast<const float*>(pr.offset) + off_base;
+          oy = __ldg(bp); ox = __ldg(bp + pr.off_sc); mk = __ldg(bp + 2 * pr.off_sc); r3 = __ldg(bp + 3 * pr.off_sc);
+        }
+        return;
+      }
       const int tap_ = it_ / p.dg, g_ = it_ - tap_ * p.dg;
       if (has_off) {
         const int64_t o = off_base + (int64_t)(g_ * 2 * K + 2 * tap_) * pr.off_sc;
@@ -240,10 +266,25 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       }
     };
     // DCN border rule: the sample is 0 outside (-1, H) x (-1, W); corners outside the map add 0.
-    auto compute_meta = [&](int it_, float oy, float ox, float mk) {
+    auto compute_meta = [&](int it_, float oy, float ox, float mk, float r3) {
       const int buf = it_ % META_BUFS;
       const int tap_ = it_ / p.dg, g_ = it_ - tap_ * p.dg;
       const int ti = tap_ / p.kw, tj = tap_ - ti * p.kw;
+      if (FCB) {
+        // (oy, ox, mk, r3) hold the box deltas (t_x, t_y, t_w, t_h)
+        const float tx = oy, ty = ox, tw_ = mk, th_ = r3;
+        if (fcb_ada) {
+          const float4* fw = reinterpret_cast<const float4*>(smem + L.fcb_w) + (g_ * 2 * K + 2 * tap_);
+          const float4 wy = fw[0], wx = fw[1];
+          oy = fmaf(wy.w, th_, fmaf(wy.z, tw_, fmaf(wy.y, ty, wy.x * tx)));
+          ox = fmaf(wx.w, th_, fmaf(wx.z, tw_, fmaf(wx.y, ty, wx.x * tx)));
+        } else {
+          // Featurealign.py:46-69: centre shift 0.1 * t * k, scale (exp(0.2 * t) - 1) * (tap index - k/2)
+          oy = 0.1f * ty * (float)p.kh + (__expf(0.2f * th_) - 1.f) * (float)(ti - p.kh / 2);
+          ox = 0.1f * tx * (float)p.kw + (__expf(0.2f * tw_) - 1.f) * (float)(tj - p.kw / 2);
+        }
+        mk = 1.f;
+      }
       if (PLAIN) {
         // regular convolution: the tap's pixel itself, or the zero page when it lies in the padding
         if (cg == 0) {
@@ -355,11 +396,11 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     };
 
     GTask S[D];                             // task (kb, j) lives in S[j % D]; D tasks are in flight per thread
-    float r_oy, r_ox, r_mk;
+    float r_oy, r_ox, r_mk, r_3;
     // prologue: metadata of iteration 0, then the first D gather tasks of K block 0
-    load_raw(0, r_oy, r_ox, r_mk);
-    compute_meta(0, r_oy, r_ox, r_mk);
-    load_raw(1, r_oy, r_ox, r_mk);
+    load_raw(0, r_oy, r_ox, r_mk, r_3);
+    compute_meta(0, r_oy, r_ox, r_mk, r_3);
+    load_raw(1, r_oy, r_ox, r_mk, r_3);
     named_barrier_sync(1, PT);
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -375,8 +416,8 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       if (cc == 0 && it + 1 < n_iter) {
         // metadata one iteration ahead: buffer (it+1) % 3 was last read by the gather of iteration it-2, which
         // every thread finished before it arrived at the previous barrier
-        compute_meta(it + 1, r_oy, r_ox, r_mk);
-        load_raw(it + 2, r_oy, r_ox, r_mk);
+        compute_meta(it + 1, r_oy, r_ox, r_mk, r_3);
+        load_raw(it + 2, r_oy, r_ox, r_mk, r_3);
         named_barrier_sync(1, PT);
       }
       int nit = it, ncc = cc + 1;
@@ -549,12 +590,12 @@ int pick_block_n(int out_c) {
   return 0;
 }
 
-SmemAttrCache g_smem_attr[16];         // one per instantiation below
+SmemAttrCache g_smem_attr[24];         // one per instantiation below
 
-template <int M_TILES, int PW, int D, bool PAIR, bool PLAIN>
+template <int M_TILES, int PW, int D, bool PAIR, int MODE>
 int launch_t(const TcArgs& args, const CUtensorMap& tmap, dim3 grid, int smem_bytes, cudaStream_t stream) {
-  constexpr int slot = ((M_TILES - 1) * 2 + (PW == 16 ? 1 : 0)) * 4 + (PAIR ? 2 : 0) + (PLAIN ? 1 : 0);
-  auto kernel = dcn_tc_kernel<M_TILES, PW, D, PAIR, PLAIN>;
+  constexpr int slot = (((M_TILES - 1) * 2 + (PW == 16 ? 1 : 0)) * 2 + (PAIR ? 1 : 0)) * 3 + MODE;
+  auto kernel = dcn_tc_kernel<M_TILES, PW, D, PAIR, MODE>;
   const int rc = ensure_dynamic_smem(kernel, smem_bytes, g_smem_attr[slot]);
   if (rc != STM_OK) return rc;
   cudaLaunchConfig_t cfg{};
@@ -582,13 +623,15 @@ int launch_t(const TcArgs& args, const CUtensorMap& tmap, dim3 grid, int smem_by
 // launcher and by stm_deform_conv2d_variant().
 struct TcPlan {
   int block_n, n_tiles, m_tiles, pw, stages, smem_bytes, tmem_cols, blocks, grid_x;
-  bool two_ctas, pair, plain;
+  bool two_ctas, pair, plain, fcb;
 };
 
 int make_plan(const StmDcnConv* conv, const DcnParams& p, TcPlan* out) {
   TcPlan pl;
   pl.block_n = pick_block_n(p.out_c);
   pl.plain = (p.flags & STM_DCN_ZERO_OFFSET) != 0;
+  pl.fcb = !pl.plain && (p.flags & (STM_DCN_FCB_ADA | STM_DCN_FCB_ALI)) != 0;
+  const int fcb_floats = pl.fcb ? p.dg * 2 * p.kh * p.kw * 4 : 0;
   int64_t rows = 0;
   for (int i = 0; i < p.n_probs; ++i) rows += p.prob[i].m_total;
   pl.n_tiles = p.out_c / pl.block_n;
@@ -638,9 +681,10 @@ int make_plan(const StmDcnConv* conv, const DcnParams& p, TcPlan* out) {
   pl.tmem_cols = cols;
   // pipeline depth: as many stages as fit while leaving L1 some room for the gather's corner reuse
   int budget = pl.m_tiles == 2 ? 172 * 1024 : (pl.two_ctas ? (pl.pair ? 82 * 1024 : 110 * 1024) : 132 * 1024);
+  budget += (fcb_floats * 4 + 15) & ~15;
   if ((conv->flags & STM_DCN_HINT_DEEP_PIPE) != 0) budget = 200 * 1024;
   auto total = [&](int st) {
-    return pl.m_tiles == 2 ? SmemLayout<2>(pl.block_n, st, pl.pair).total : SmemLayout<1>(pl.block_n, st, pl.pair).total;
+    return pl.m_tiles == 2 ? SmemLayout<2>(pl.block_n, st, pl.pair, fcb_floats).total : SmemLayout<1>(pl.block_n, st, pl.pair, fcb_floats).total;
   };
   pl.stages = MAX_STAGES;
   for (; pl.stages > 2; --pl.stages)
@@ -686,16 +730,19 @@ int dcn_tc_variant(const StmDcnConv* conv, const DcnParams& p, char* buf, size_t
   TcPlan pl;
   const int rc = make_plan(conv, p, &pl);
   if (rc != STM_OK) return rc;
-  snprintf(buf, len, "tcgen05 rows=%d n=%d pair=%d plain=%d producer_warps=%d stages=%d ctas_per_sm=%d grid=%dx%d", TILE_M * pl.m_tiles,
-           pl.block_n, pl.pair ? 1 : 0, pl.plain ? 1 : 0, pl.pw, pl.stages, pl.two_ctas ? 2 : 1, pl.grid_x, pl.n_tiles);
+  snprintf(buf, len, "tcgen05 rows=%d n=%d pair=%d plain=%d fcb=%d producer_warps=%d stages=%d ctas_per_sm=%d grid=%dx%d", TILE_M * pl.m_tiles,
+           pl.block_n, pl.pair ? 1 : 0, pl.plain ? 1 : 0, pl.fcb ? 1 : 0, pl.pw, pl.stages, pl.two_ctas ? 2 : 1, pl.grid_x, pl.n_tiles);
   return STM_OK;
 }
+
+static bool pl_fcb_needs_weight(const DcnParams& p) { return (p.flags & STM_DCN_FCB_ADA) != 0 && (p.flags & STM_DCN_ZERO_OFFSET) == 0; }
 
 int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, cudaStream_t stream) {
   TcArgs args;
   args.p = p_in;
   DcnParams& p = args.p;
   p.flags &= 0xffff;
+  if (pl_fcb_needs_weight(p) && p.fcb_w == nullptr) { set_error("FCB(ada) needs the conv_offset weight"); return STM_ERR_INVALID_ARGUMENT; }
   if (conv->offset_dtype == STM_BF16) p.flags |= FLAG_OFFSETS_BF16;
   TcPlan pl;
   const int prc = make_plan(conv, p, &pl);
@@ -727,16 +774,22 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return STM_ERR_CUDA; }
 
   const dim3 grid((unsigned)pl.grid_x, (unsigned)pl.n_tiles);
-#define STM_GO(MT, PW_, D_, PAIR_, PLAIN_) return launch_t<MT, PW_, D_, PAIR_, PLAIN_>(args, tmap, grid, pl.smem_bytes, stream)
+#define STM_GO(MT, PW_, D_, PAIR_, MODE_) return launch_t<MT, PW_, D_, PAIR_, MODE_>(args, tmap, grid, pl.smem_bytes, stream)
   if (pl.plain) {                      // regular convolution: every task of the next K block in flight (4 registers each)
-    if (pl.m_tiles == 2) { if (pl.pair) STM_GO(2, 16, 4, true, true); STM_GO(2, 16, 4, false, true); }
-    if (pl.pair) STM_GO(1, 16, 2, true, true);
-    STM_GO(1, 16, 2, false, true);
+    if (pl.m_tiles == 2) { if (pl.pair) STM_GO(2, 16, 4, true, 1); STM_GO(2, 16, 4, false, 1); }
+    if (pl.pair) STM_GO(1, 16, 2, true, 1);
+    STM_GO(1, 16, 2, false, 1);
   }
-  if (pl.m_tiles == 2) { if (pl.pair) STM_GO(2, 16, 2, true, false); STM_GO(2, 16, 2, false, false); }
-  if (pl.pw == 8) { if (pl.pair) STM_GO(1, 8, 2, true, false); STM_GO(1, 8, 2, false, false); }   // 4 gather tasks per thread per K block, two CTAs per SM
-  if (pl.pair) STM_GO(1, 16, 2, true, false);
-  STM_GO(1, 16, 2, false, false);                           // 2 tasks
+  if (pl.fcb) {                        // box-guided offsets derived in the metadata stage
+    if (pl.m_tiles == 2) { if (pl.pair) STM_GO(2, 16, 2, true, 2); STM_GO(2, 16, 2, false, 2); }
+    if (pl.pw == 8) { if (pl.pair) STM_GO(1, 8, 2, true, 2); STM_GO(1, 8, 2, false, 2); }
+    if (pl.pair) STM_GO(1, 16, 2, true, 2);
+    STM_GO(1, 16, 2, false, 2);
+  }
+  if (pl.m_tiles == 2) { if (pl.pair) STM_GO(2, 16, 2, true, 0); STM_GO(2, 16, 2, false, 0); }
+  if (pl.pw == 8) { if (pl.pair) STM_GO(1, 8, 2, true, 0); STM_GO(1, 8, 2, false, 0); }   // 4 gather tasks per thread per K block, two CTAs per SM
+  if (pl.pair) STM_GO(1, 16, 2, true, 0);
+  STM_GO(1, 16, 2, false, 0);                           // 2 tasks
 #undef STM_GO
 }
 

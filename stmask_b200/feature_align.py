@@ -35,6 +35,7 @@ class FeatureAlign(nn.Module):
         self.conv_adaption = DeformConv2d(in_channels, in_channels, kernel_size=self.kernel_size, padding=self.padding,
                                           deform_groups=deformable_groups)
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=self.kernel_size, padding=self.padding)
+        self._fused = None          # None: untried, True / False: the fused-offset tcgen05 path applies / does not
 
     def init_weights(self, bias_value=0):
         if self.use_pred_offset:
@@ -53,9 +54,22 @@ class FeatureAlign(nn.Module):
                          outs: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
         """relu(conv_adaption(x, offset)) for every level, one launch."""
         ops._no_grad_inputs(self.conv_adaption.weight, *xs)
-        offs = [self.offsets(s) for s in shapes]
         spec = self.conv_adaption.spec()
         wp = self.conv_adaption._cache.weight(self.conv_adaption.weight, spec, xs[0].dtype)
+        if self._fused is not False and xs[0].dtype == torch.bfloat16 and (self.use_pred_offset or self.deformable_groups == 1):
+            # tcgen05 path: the offsets are derived inside the sampling kernel from the box deltas — no offset tensors,
+            # no offset kernels.  Shapes that need the CUDA-core kernel answer STM_ERR_UNSUPPORTED once; remember it.
+            try:
+                ys = ops.deform_conv2d_fcb_multi(list(xs), [s.detach() for s in shapes], wp, spec,
+                                                 self.conv_offset.weight if self.use_pred_offset else None, relu=True, outs=outs)
+                self._fused = True
+                return ys
+            except ops.L.StmError as e:
+                if "status -2" not in str(e):
+                    raise
+                if self._fused is None:
+                    self._fused = False
+        offs = [self.offsets(s) for s in shapes]
         return ops.deform_conv2d_multi(list(xs), offs, None, wp, None, spec, relu=True, outs=outs)
 
     def forward_levels(self, xs: Sequence[torch.Tensor], shapes: Sequence[torch.Tensor]) -> List[torch.Tensor]:

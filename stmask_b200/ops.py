@@ -315,6 +315,71 @@ def deform_conv2d_multi(xs: Sequence[torch.Tensor], offsets: Sequence[Optional[t
     return ys
 
 
+def deform_conv2d_fcb_multi(xs: Sequence[torch.Tensor], deltas: Sequence[torch.Tensor], w_packed: torch.Tensor, spec: ConvSpec,
+                            fcb_weight: Optional[torch.Tensor], *, relu: bool = True,
+                            outs: Optional[Sequence[torch.Tensor]] = None, hint: int = 0) -> List[torch.Tensor]:
+    """FeatureAlign's deformable conv over several FPN levels in ONE launch with the offsets derived INSIDE the kernel
+    from the regressed box deltas (`deltas[i]`: [B, 4, H, W] = (t_x, t_y, t_w, t_h), any strides, fp32 or bf16):
+    FCB(ada) when `fcb_weight` (the 1x1 conv_offset weight [dg*2*kh*kw, 4, 1, 1]) is given, FCB(ali) (closed form)
+    when it is None.  tcgen05 backend only — raises StmError (status -2) for shapes that need the CUDA-core kernel."""
+    n = len(xs)
+    if n == 0:
+        return []
+    if n > L.DCN_MAX_PROBLEMS or len(deltas) != n:
+        raise ValueError("xs / deltas length mismatch or too many feature maps")
+    _no_grad_inputs(*xs, *deltas)
+    dev = w_packed.device
+    probs = (L.StmDcnProblem * n)()
+    keep, ys = [], []
+    odt = None
+    for i in range(n):
+        x, dl = xs[i], deltas[i]
+        _require_cuda(x, "x")
+        _require_cuda(dl, "box deltas")
+        if x.dim() != 4 or x.shape[1] != spec.in_c:
+            raise ValueError(f"x must be [B, {spec.in_c}, H, W], got {tuple(x.shape)}")
+        b, _, h, w = x.shape
+        ho, wo = spec.out_hw(h, w)
+        if tuple(dl.shape) != (b, 4, ho, wo):
+            raise ValueError(f"box deltas shape {tuple(dl.shape)} != {(b, 4, ho, wo)}")
+        d_off = _dt(dl, "box deltas")
+        if odt is None:
+            odt = d_off
+        elif odt != d_off:
+            raise TypeError("all box-delta tensors of one launch must share a dtype")
+        xn = to_nhwc(x)
+        if outs is not None:
+            y = outs[i]
+            if tuple(y.shape) != (b, spec.out_c, ho, wo) or y.dtype != x.dtype or y.stride(1) != 1:
+                raise ValueError("preallocated output must be a channels-last tensor of the right shape/dtype")
+        else:
+            y = torch.empty((b, spec.out_c, ho, wo), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
+        keep += [xn, dl, y]
+        ys.append(y)
+        p = probs[i]
+        p.batch, p.in_h, p.in_w, p.out_h, p.out_w = b, h, w, ho, wo
+        p.x = xn.data_ptr()
+        p.x_stride_n, p.x_stride_h, p.x_stride_w = xn.stride(0), xn.stride(2), xn.stride(3)
+        p.offset = dl.data_ptr()
+        p.off_stride_n, p.off_stride_c, p.off_stride_h, p.off_stride_w = dl.stride()
+        p.y = y.data_ptr()
+        p.y_stride_n, p.y_stride_h, p.y_stride_w = y.stride(0), y.stride(2), y.stride(3)
+    fw = None
+    if fcb_weight is not None:
+        fw = fcb_weight.detach().reshape(-1, 4).float().contiguous()
+        if fw.shape[0] != spec.deform_groups * 2 * spec.kernel[0] * spec.kernel[1]:
+            raise ValueError("conv_offset weight does not match kernel_size / deform_groups")
+    flags = (L.DCN_RELU if relu else 0) | (L.DCN_FCB_ADA if fw is not None else L.DCN_FCB_ALI)
+    flags |= int(hint) & (L.DCN_HINT_ROWS128 | L.DCN_HINT_ROWS256 | L.DCN_HINT_NO_PAIR | L.DCN_HINT_TWO_CTAS)
+    conv = spec.c_struct(_dt(xs[0], "x"), odt, flags, L.BACKEND_AUTO)
+    with torch.cuda.device(dev):
+        rc = L.lib().stm_deform_conv2d_fcb_fwd(C.byref(conv), probs, n, w_packed.data_ptr(), None,
+                                               fw.data_ptr() if fw is not None else None, None, 0,
+                                               torch.cuda.current_stream(dev).cuda_stream)
+    L.check(rc, "stm_deform_conv2d_fcb_fwd")
+    return ys
+
+
 def deform_conv2d_backend(x_shape: Sequence[int], spec: ConvSpec, dtype: torch.dtype, backend: str = "auto") -> str:
     """Which kernel family a call would use ('simt' / 'tcgen05') — shape-only query."""
     b, _, h, w = x_shape
@@ -543,6 +608,55 @@ def correlation(x1: torch.Tensor, x2: torch.Tensor, patch_size: int = 11, dilati
                                          fb.data_ptr() if fb is not None else None, out.data_ptr(), _stream(x1))
     L.check(rc, "stm_correlation_fwd")
     return out
+
+
+def correlation_multi(x1s: Sequence[torch.Tensor], x2s: Sequence[torch.Tensor], patch_size: int = 11, dilation_patch: int = 1, *,
+                      scale: float = 1.0, leaky_slope: Optional[float] = None, relu: bool = False,
+                      padded: bool = True) -> List[torch.Tensor]:
+    """Cost volumes of several feature maps (the FPN levels P3..P7) in ONE launch: out[i] is the channels-last bf16
+    cost volume of (x1s[i], x2s[i]).  `padded` (default): rows of padded_channels = ceil(P*P / 8) * 8 channels (128 for
+    P = 11; channels [P*P, 128) are zeros) so that every pixel row is 256 bytes and is written with 16-byte stores —
+    `out[i][:, :P*P]` is the reference's `[B, P*P, H, W]` view; `padded=False`: exactly P*P channels (element-wise stores).
+    bf16 / tcgen05 only."""
+    n = len(x1s)
+    if n == 0:
+        return []
+    if n != len(x2s) or n > 8:
+        raise ValueError("x1s / x2s must have the same length (<= 8)")
+    P, d = int(patch_size), int(dilation_patch)
+    if P < 1 or P % 2 == 0 or d < 1:
+        raise ValueError("patch_size must be odd and positive, dilation_patch >= 1")
+    flags = (L.CORR_LEAKY_RELU if leaky_slope is not None else 0) | (L.CORR_RELU if relu else 0)
+    ch = (P * P + 7) // 8 * 8 if padded else P * P
+    descs = (L.StmCorrDesc * n)()
+    p1, p2, po = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
+    keep, outs = [], []
+    for i, (x1, x2) in enumerate(zip(x1s, x2s)):
+        _require_cuda(x1, "input1")
+        _require_cuda(x2, "input2")
+        if x1.dim() != 4 or x1.shape != x2.shape or x1.dtype != torch.bfloat16 or x2.dtype != torch.bfloat16:
+            raise TypeError("correlation_multi takes pairs of equal-shape 4-D bf16 tensors")
+        a, b = to_nhwc(x1), to_nhwc(x2)
+        bsz, c, h, w = a.shape
+        out = torch.empty((bsz, ch, h, w), dtype=torch.bfloat16, device=a.device, memory_format=torch.channels_last)
+        keep += [a, b]
+        outs.append(out)
+        q = descs[i]
+        q.batch, q.h, q.w, q.c = bsz, h, w, c
+        q.patch, q.dilation_patch = P, d
+        q.dtype = q.out_dtype = L.STM_BF16
+        q.flags, q.backend = flags, L.BACKEND_TCGEN05
+        q.scale, q.leaky_slope = float(scale), float(leaky_slope or 0.0)
+        q.x1_stride_n, q.x1_stride_h, q.x1_stride_w = a.stride(0), a.stride(2), a.stride(3)
+        q.x2_stride_n, q.x2_stride_h, q.x2_stride_w = b.stride(0), b.stride(2), b.stride(3)
+        q.out_stride_n, q.out_stride_c, q.out_stride_h, q.out_stride_w = out.stride()
+        q.feat_c_offset = ch if padded else 0
+        p1[i], p2[i], po[i] = a.data_ptr(), b.data_ptr(), out.data_ptr()
+    dev = outs[0].device
+    with torch.cuda.device(dev):
+        rc = L.lib().stm_correlation_multi_fwd(descs, p1, p2, po, n, torch.cuda.current_stream(dev).cuda_stream)
+    L.check(rc, "stm_correlation_multi_fwd")
+    return outs
 
 
 _checked_indices = {}

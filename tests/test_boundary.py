@@ -189,7 +189,7 @@ def test_launch_plan_is_a_pure_function_of_the_call():
     fpn = [(72, 256, h, w) for h, w in ((48, 80), (24, 40), (12, 20), (6, 10), (3, 5))]
     fcb = ops.ConvSpec(256, 256, (3, 5), 1, (1, 2))
     v = ops.deform_conv2d_variant(fpn, fcb, torch.bfloat16)
-    assert "tcgen05 rows=128 n=256 pair=1 plain=0 producer_warps=8" in v and "ctas_per_sm=2" in v, v
+    assert "tcgen05 rows=128 n=256 pair=1 plain=0 fcb=0 producer_warps=8" in v and "ctas_per_sm=2" in v, v
     assert "rows=256 n=256 pair=0" in ops.deform_conv2d_variant(fpn, fcb, torch.bfloat16, hint=_lib.DCN_HINT_NO_PAIR)
     assert "rows=256 n=256 pair=1" in ops.deform_conv2d_variant(fpn, fcb, torch.bfloat16, hint=_lib.DCN_HINT_ROWS256)
     assert "rows=128 n=256 pair=1" in ops.deform_conv2d_variant(fpn, fcb, torch.bfloat16, hint=_lib.DCN_HINT_ROWS128)

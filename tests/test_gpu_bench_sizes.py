@@ -162,3 +162,80 @@ def test_correlation_sweep_vs_oracle(cuda_device, d):
                                   out_dtype=torch.float32)
             assert got.shape == (8, 121, h, w)
             assert rel_err(got.cpu().numpy(), want) <= TOL, (h, w, d, cl)
+
+
+@pytest.mark.parametrize("d", [1, 2])
+@pytest.mark.parametrize("padded", [True, False])
+def test_correlation_grouped_multi_level_launch_vs_oracle(cuda_device, d, padded):
+    """BASELINE.json configs[1]: the cost volumes of P3..P7 at batch 8 in ONE launch, channels-last."""
+    ops, L = _ops()
+    rng = np.random.default_rng(50 + d)
+    x1s = [q(rng.standard_normal((8, 256, h, w))) for h, w in FPN]
+    x2s = [q(rng.standard_normal((8, 256, h, w))) for h, w in FPN]
+    n0 = L.launch_count()
+    outs = ops.correlation_multi([dev(a, BF16, cuda_device) for a in x1s], [dev(b, BF16, cuda_device) for b in x2s], 11, d,
+                                 scale=1.0 / 256, leaky_slope=0.1, padded=padded)
+    torch.cuda.synchronize()
+    assert L.launch_count() - n0 == 1
+    for (h, w), a, b, o in zip(FPN, x1s, x2s, outs):
+        assert o.shape == (8, 128 if padded else 121, h, w) and o.stride(1) == 1
+        want = oracle.correlate(a, b, 11, d)
+        assert rel_err(o[:, :121].float().cpu().numpy(), want) <= TOL, (h, w, d)
+        if padded:
+            assert float(o[:, 121:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------
+# FCB with the offsets derived INSIDE the sampling kernel from the box deltas (SURVEY.md 8f rank 2)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,dg", [("ada", 1), ("ada", 4), ("ali", 1)])
+@pytest.mark.parametrize("kernel", [(3, 3), (3, 5), (5, 3)], ids=lambda k: f"{k[0]}x{k[1]}")
+def test_fcb_fused_offsets_vs_oracle(cuda_device, kernel, mode, dg):
+    """stm_deform_conv2d_fcb_fwd over P3..P7 at batch 8 (one launch, no offset tensors) against the oracle's
+    FeatureAlign restatement (offsets from the deltas in fp64, then the deformable conv + ReLU); also every CTA shape."""
+    ops, L = _ops()
+    kh, kw = kernel
+    pad = ((kh - 1) // 2, (kw - 1) // 2)
+    rng = np.random.default_rng(kh * 7 + kw * 3 + dg + (1 if mode == "ada" else 0))
+    spec = ops.ConvSpec(256, 256, kernel, 1, pad, 1, 1, dg)
+    w = q(rng.standard_normal((256, 256, kh, kw)) / np.sqrt(256 * kh * kw))
+    xs = [q(rng.standard_normal((8, 256, h, ww))) for h, ww in FPN]
+    deltas = [rng.standard_normal((8, 4, h, ww)).astype(np.float32) for h, ww in FPN]
+    w_off = (rng.standard_normal((dg * 2 * kh * kw, 4, 1, 1)) * 0.5).astype(np.float32) if mode == "ada" else None
+    wants = [oracle.feature_align(x, dl, w, kernel, w_offset=w_off, deform_groups=dg)[0] for x, dl in zip(xs, deltas)]
+    wp = ops.pack_weight(dev(w, BF16, cuda_device, cl=False), spec, BF16)
+    xd = [dev(x, BF16, cuda_device) for x in xs]
+    dd = [dev(dl, torch.float32, cuda_device, cl=i % 2 == 0) for i, dl in enumerate(deltas)]      # NHWC and NCHW delta tensors
+    wod = dev(w_off, torch.float32, cuda_device, cl=False) if w_off is not None else None
+    n0 = L.launch_count()
+    for hint in (0, L.DCN_HINT_NO_PAIR, L.DCN_HINT_ROWS128 | L.DCN_HINT_NO_PAIR, L.DCN_HINT_ROWS256):
+        ys = ops.deform_conv2d_fcb_multi(xd, dd, wp, spec, wod, relu=True, hint=hint)
+        torch.cuda.synchronize()
+        for lvl, (y, want) in enumerate(zip(ys, wants)):
+            err = rel_err(y.float().cpu().numpy(), want)
+            assert err <= TOL, (mode, hint, lvl, err)
+    assert L.launch_count() - n0 == 4                               # one kernel per call: no offset kernels
+
+
+def test_feature_align_module_uses_the_fused_path(cuda_device):
+    from stmask_b200.feature_align import FeatureAlign
+    ops, L = _ops()
+    rng = np.random.default_rng(3)
+    for mode in ("ada", "ali"):
+        m = FeatureAlign(256, 41, (3, 5), deformable_groups=1, use_pred_offset=mode == "ada").to(cuda_device)
+        torch.nn.init.normal_(m.conv_adaption.weight, std=0.02)
+        if mode == "ada":
+            torch.nn.init.normal_(m.conv_offset.weight, std=0.5)
+        m.conv_adaption.to(BF16)
+        xs = [dev(q(rng.standard_normal((2, 256, h, w))), BF16, cuda_device) for h, w in FPN[1:4]]
+        bs = [dev(rng.standard_normal((2, 4, h, w)), torch.float32, cuda_device, cl=False) for h, w in FPN[1:4]]
+        n0 = L.launch_count()
+        with torch.no_grad():
+            fused = m.calibrate_levels(xs, bs)
+        assert m._fused is True and L.launch_count() - n0 == 1
+        with torch.no_grad():
+            two_step = ops.deform_conv2d_multi(xs, [m.offsets(b) for b in bs], None,
+                                               m.conv_adaption._cache.weight(m.conv_adaption.weight, m.conv_adaption.spec(), BF16), None,
+                                               m.conv_adaption.spec(), relu=True)
+        for a, b in zip(fused, two_step):
+            assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) <= 2e-3     # same samples; fp32 offsets either way
