@@ -20,6 +20,8 @@ Sources of truth:
   model_r50.npz         BASELINE.json configs[0]: the reference's own STMask (R50-DCN-FPN FCA+TF, STMask.py:205-329) on a
                         synthetic 2-frame clip via oracle/ref_model.py: inputs / outputs of all 7 backbone DCN call sites,
                         the correlate / concat / RoIAlign / TemporalNet call sites of CandidateShift and the shifted boxes
+  prediction_head.npz   the reference's own PredictionModule_FC.forward (R101 FCA+FCB(ada) head, shared over five levels):
+                        loc / centerness / conf / mask_coeff / track / priors, weights rebuilt from the recorded seed
   temporal_net.npz      the reference's own TemporalNet.forward + bbox_feat_extractor (track_to_segment_head.py:10-37,
                         65-88) on a 633-channel concat; the 40 MB of weights are rebuilt from the recorded seed
                         (default nn init in construction order) and pinned by per-parameter checksums
@@ -290,6 +292,40 @@ def _temporal_net():
                         h1_mean=h1.mean(dim=(2, 3)).numpy())
 
 
+HEAD_SEED = 20260303
+HEAD_LEVELS = [(12, 20), (6, 10), (3, 5), (2, 3), (1, 2)]
+
+
+def _prediction_head():
+    """The reference's own PredictionModule_FC.forward (prediction_head_FC.py:129-222) of the R101 FCA+FCB(ada) config
+    (`STMask_plus_base_ada_config`), applied to five FPN levels with shared weights and concatenated over the levels the
+    way STMask.forward_single does (STMask.py:245-279).  Weights: default init under a recorded seed (7.6 M parameters:
+    rebuilt, not stored; pinned by checksums)."""
+    from . import ref_model
+    ref_model._install_stubs()
+    import STMask  # noqa: F401  (initialises the reference's package imports)
+    from datasets.config import cfg, set_cfg
+    set_cfg("STMask_plus_base_ada_config")
+    import layers.modules.prediction_head_FC as ph
+    cfg.mask_dim, cfg.num_heads = 32, 5
+    torch.manual_seed(HEAD_SEED)
+    head = ph.PredictionModule_FC(256, 256, deform_groups=1, pred_aspect_ratios=cfg.backbone.pred_aspect_ratios[0],
+                                  pred_scales=cfg.backbone.pred_scales[0], parent=None)
+    head.eval()
+    g = torch.Generator().manual_seed(11)
+    xs = [torch.randn(1, 256, h, w, generator=g).bfloat16().float() for h, w in HEAD_LEVELS]
+    outs = {}
+    with torch.no_grad():
+        for x in xs:
+            for k, v in head(x).items():
+                outs.setdefault(k, []).append(v)
+    res = {k: torch.cat(v, 1).numpy() for k, v in outs.items() if k != "T2S_feat"}
+    res["T2S_feat0"] = outs["T2S_feat"][0].numpy()
+    cs = np.array([[float(v.double().sum()), float(v.double().abs().sum())] for v in head.state_dict().values()], np.float64)
+    np.savez_compressed(os.path.join(OUT, "prediction_head.npz"), seed=np.int64(HEAD_SEED), checksums=cs,
+                        **{f"x{i}": x.numpy() for i, x in enumerate(xs)}, **res)
+
+
 def _model_r50():
     """BASELINE.json configs[0] / SURVEY.md 8(c) "Model:" known answer: the reference's own STMask (R50-DCN-FPN
     FCA+TF) on a synthetic 2-frame clip through oracle/ref_model.py; every hot-op call site of frame 2."""
@@ -314,6 +350,7 @@ def main():
     _roi_align()
     _temporal_net()
     _model_r50()
+    _prediction_head()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -100,3 +100,46 @@ def test_temporal_fusion_call_sites(cuda_device, dtype):
     dec[:, :2] -= dec[:, 2:] / 2
     dec[:, 2:] += dec[:, :2]
     assert np.abs(dec.numpy() - z["shift.box_ref_shift"]).max() <= (1e-5 if dtype == torch.float32 else 2e-3)
+
+
+# ------------------------------------------------------------------------------------------
+# FCA / FCB prediction head over P3..P7 as grouped tcgen05 launches (SURVEY.md 8f rank 3, and rank 2's prior cache)
+# ------------------------------------------------------------------------------------------
+HEAD_KEYS = ("loc", "centerness", "conf", "mask_coeff", "track")
+
+
+def _golden_head(device):
+    from stmask_b200.prediction_head import PredictionHeadFC
+    z = load_golden("prediction_head.npz")
+    torch.manual_seed(int(z["seed"]))
+    head = PredictionHeadFC(256, 41, 32, 128, fcb="ada")
+    cs = np.array([[float(v.double().sum()), float(v.double().abs().sum())] for v in head.state_dict().values()])
+    assert np.allclose(cs, z["checksums"], rtol=1e-9, atol=1e-9)
+    xs = [z[f"x{i}"] for i in range(5)]
+    return z, head.to(device), xs
+
+
+def test_prediction_head_fp32_vs_reference(cuda_device):
+    z, head, xs = _golden_head(cuda_device)
+    out = head.forward_levels([dev(x, torch.float32, cuda_device, cl=True) for x in xs])
+    for k in HEAD_KEYS:
+        assert out[k].shape == z[k].shape, k
+        assert rel_err(out[k].cpu().numpy(), z[k]) <= 1e-4, (k, rel_err(out[k].cpu().numpy(), z[k]))
+    assert np.array_equal(out["priors"].cpu().numpy(), z["priors"])
+    assert rel_err(out["T2S_feat"][0].cpu().numpy(), z["T2S_feat0"]) <= 1e-4
+
+
+def test_prediction_head_bf16_grouped_tcgen05_launches(cuda_device):
+    """bf16: every conv of the head is ONE tcgen05 launch over the five levels (24 launches in all); <= 1e-2 against
+    fp32 math on the same bf16-rounded weights (the CUDA-core path, pinned to the reference by the test above)."""
+    from stmask_b200 import _lib
+    z, head, xs = _golden_head(cuda_device)
+    head16 = head.to(torch.bfloat16)
+    xd = [dev(x, torch.bfloat16, cuda_device, cl=True) for x in xs]
+    head16.forward_levels(xd)                                       # packs the weights
+    n0 = _lib.launch_count()
+    got = head16.forward_levels(xd)
+    assert _lib.launch_count() - n0 == 1 + 1 + 4 + 3 * 5
+    ref = head16.float().forward_levels([t.float() for t in xd])
+    for k in HEAD_KEYS:
+        assert rel_err(got[k].cpu().numpy(), ref[k].cpu().numpy()) <= 1e-2, (k, rel_err(got[k].cpu().numpy(), ref[k].cpu().numpy()))
