@@ -160,7 +160,9 @@ class PredictionHeadFC(nn.Module):
         for l, d in enumerate(per_level):
             b = xs[l].shape[0]
             out["loc"].append(torch.cat(d["loc"], -1).reshape(b, -1, 4))
-            out["centerness"].append(torch.tanh(torch.cat(d["ctr"], -1).reshape(b, -1, 1)))
+            # the reference concatenates the per-kernel centerness maps along dim 1 of [B, H, W, 1] (prediction_head_FC.py:190):
+            # kernel-major order inside a level, unlike loc / conf / mask / track (pixel-major, kernels innermost)
+            out["centerness"].append(torch.tanh(torch.cat(d["ctr"], 1).reshape(b, -1, 1)))
             out["conf"].append(torch.cat(d["conf"], -1).reshape(b, -1, self.num_classes))
             out["mask_coeff"].append(torch.cat(d["mask"], -1).reshape(b, -1, self.mask_dim))
             out["track"].append(F.normalize(torch.cat(d["track"], -1).reshape(b, -1, self.embed_dim), dim=-1))

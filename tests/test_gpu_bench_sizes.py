@@ -239,4 +239,4 @@ def test_feature_align_module_uses_the_fused_path(cuda_device):
                                                m.conv_adaption._cache.weight(m.conv_adaption.weight, m.conv_adaption.spec(), BF16), None,
                                                m.conv_adaption.spec(), relu=True)
         for a, b in zip(fused, two_step):
-            assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) <= 2e-3     # same samples; fp32 offsets either way
+            assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) <= 1e-2     # same samples up to fp32 rounding of the offsets: bf16 ulps
