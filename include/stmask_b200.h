@@ -13,6 +13,8 @@
  *   stm_fcb_ada_offsets     <- the 1x1 conv_offset on box deltas    (layers/modules/Featurealign.py:20-25,44)
  *   stm_roi_align_fwd       <- mmcv.ops.roi_align as bbox_feat_extractor calls it
  *                              (layers/modules/track_to_segment_head.py:65-88)
+ *   stm_detect_fast_nms_fwd <- generate_candidate + Detect_TF.cc_fast_nms, batched and sync-free
+ *                              (layers/functions/TF_utils.py:54-82, layers/functions/detection_TF.py:85-134)
  *   stm_pool_fc_fwd         <- TemporalNet's AvgPool2d(7x7) + fc + fc_coeff tail; its three 3x3 convs are
  *                              stm_deform_conv2d_fwd with STM_DCN_ZERO_OFFSET
  *                              (layers/modules/track_to_segment_head.py:10-37)
@@ -268,6 +270,23 @@ typedef struct StmRoiAlignDesc {
  * out[r, c, i, j] = mean over the sample grid of bin (i, j) of the bilinearly interpolated feature;
  * sample points outside [-1, h] x [-1, w] contribute 0, others are clamped into the map. */
 int stm_roi_align_fwd(const StmRoiAlignDesc* desc, const void* feat, const float* rois, void* out, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Candidate generation + cross-class fast NMS for a batch of frames           */
+/* (generate_candidate, TF_utils.py:54-82; Detect_TF.cc_fast_nms,              */
+/*  detection_TF.py:85-134) — one launch, no host round trip                   */
+/* ------------------------------------------------------------------------- */
+/* conf [frames, n_priors, n_classes] class PROBABILITIES (class 0 = background), loc [frames, n_priors, 4] box
+ * regressions, centerness [frames, n_priors] or NULL, priors [n_priors, 4] (cx, cy, w, h) — all float32, contiguous.
+ * A prior is a candidate when max_{c>0} conf > conf_thresh; score = that probability x centerness; candidates are
+ * sorted by score (descending), cut to top_k (<= 256) and a candidate survives iff no higher-scoring candidate overlaps
+ * it with IoU > nms_thresh.  Outputs (device, fixed size, survivors in score order): count [frames],
+ * index / cls / score [frames, top_k], box [frames, top_k, 4] (x1, y1, x2, y2; decoded with variances 0.1 / 0.2,
+ * box_utils.py:238-283).  Entries past count[f] are left untouched. */
+int stm_detect_fast_nms_fwd(const float* conf, const float* loc, const float* centerness, const float* priors,
+                            int32_t frames, int32_t n_priors, int32_t n_classes, int32_t top_k,
+                            float conf_thresh, float nms_thresh,
+                            int32_t* count, int32_t* index, int32_t* cls, float* score, float* box, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* TemporalNet tail: y[n, :] = W * mean over the hw pixels of x[n] + b        */

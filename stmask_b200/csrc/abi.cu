@@ -343,6 +343,20 @@ int stm_correlation_multi_fwd(const StmCorrDesc* descs, const void* const* x1s, 
   return launch_corr_tc_multi(descs, x1s, x2s, nullptr, nullptr, outs, n, (cudaStream_t)stream);
 }
 
+int stm_detect_fast_nms_fwd(const float* conf, const float* loc, const float* centerness, const float* priors, int32_t frames,
+                            int32_t n_priors, int32_t n_classes, int32_t top_k, float conf_thresh, float nms_thresh,
+                            int32_t* count, int32_t* index, int32_t* cls, float* score, float* box, void* stream) {
+  clear_error();
+  STM_CHECK_ARG(frames >= 0 && n_priors > 0 && n_classes >= 2, "bad size");
+  STM_CHECK_ARG(top_k > 0 && top_k <= 256, "top_k %d outside (0, 256]", top_k);
+  STM_CHECK_ARG(n_priors <= 16384, "at most 16384 priors per frame (got %d)", n_priors);
+  if (frames == 0) return STM_OK;
+  STM_CHECK_ARG(conf && loc && priors && count && index && cls && score && box, "null pointer");
+  STM_CHECK_ARG((((uintptr_t)box) & 15) == 0, "box output must be 16-byte aligned");
+  return launch_detect_nms(conf, loc, centerness, priors, frames, n_priors, n_classes, top_k, conf_thresh, nms_thresh, count, index,
+                           cls, score, box, (cudaStream_t)stream);
+}
+
 int stm_roi_align_fwd(const StmRoiAlignDesc* d, const void* feat, const float* rois, void* out, void* stream) {
   clear_error();
   STM_CHECK_ARG(d != nullptr, "roi_align descriptor is null");

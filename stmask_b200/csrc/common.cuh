@@ -135,6 +135,9 @@ int launch_corr_tc_multi(const StmCorrDesc* descs, const void* const* x1s, const
 bool corr_tc_supported(const StmCorrDesc& d, const char** why);
 int launch_pool_fc(const void* x, int dtype, int n, int hw, int c, int64_t x_stride_n, int64_t x_stride_p, const float* w,
                    const float* b, int out_features, float* y, cudaStream_t stream);
+int launch_detect_nms(const float* conf, const float* loc, const float* centerness, const float* priors, int frames, int P, int C,
+                      int top_k, float conf_thresh, float nms_thresh, int32_t* count, int32_t* index, int32_t* cls, float* score,
+                      float* box, cudaStream_t stream);
 int launch_roi_align(const StmRoiAlignDesc& d, const void* feat, const float* rois, void* out, cudaStream_t stream);
 
 }  // namespace stm

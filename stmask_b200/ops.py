@@ -830,6 +830,35 @@ def roi_align(input: torch.Tensor, rois: torch.Tensor, output_size=7, spatial_sc
     return out
 
 
+def detect_fast_nms(conf: torch.Tensor, loc: torch.Tensor, centerness: Optional[torch.Tensor], priors: torch.Tensor, *,
+                    conf_thresh: float = 0.05, nms_thresh: float = 0.5, top_k: int = 200):
+    """Candidate generation + cross-class fast NMS for a batch of frames in one launch (TF_utils.py:54-82,
+    detection_TF.py:85-134).  conf [F, P, C] class probabilities, loc [F, P, 4], centerness [F, P] / [F, P, 1] or None,
+    priors [P, 4] / [1, P, 4].  Returns (count [F] int32, index [F, top_k] int32, cls [F, top_k] int32 (1-based),
+    score [F, top_k], box [F, top_k, 4]) — device tensors; rows are valid up to count[f]; nothing is synchronised."""
+    _require_cuda(conf, "conf")
+    if conf.dim() != 3 or loc.shape != conf.shape[:2] + (4,):
+        raise ValueError("conf must be [F, P, C] and loc [F, P, 4]")
+    f, p, c = conf.shape
+    pri = priors.reshape(-1, 4)
+    if pri.shape[0] != p:
+        raise ValueError(f"priors must hold {p} boxes")
+    cf, lc, pr = conf.float().contiguous(), loc.float().contiguous(), pri.float().contiguous()
+    ct = centerness.reshape(f, p).float().contiguous() if centerness is not None else None
+    dev = conf.device
+    count = torch.zeros(f, dtype=torch.int32, device=dev)
+    index = torch.full((f, top_k), -1, dtype=torch.int32, device=dev)
+    cls = torch.zeros((f, top_k), dtype=torch.int32, device=dev)
+    score = torch.zeros((f, top_k), dtype=torch.float32, device=dev)
+    box = torch.zeros((f, top_k, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.lib().stm_detect_fast_nms_fwd(cf.data_ptr(), lc.data_ptr(), ct.data_ptr() if ct is not None else None, pr.data_ptr(), f, p, c,
+                                             int(top_k), float(conf_thresh), float(nms_thresh), count.data_ptr(), index.data_ptr(),
+                                             cls.data_ptr(), score.data_ptr(), box.data_ptr(), _stream(conf))
+    L.check(rc, "stm_detect_fast_nms_fwd")
+    return count, index, cls, score, box
+
+
 def pool_fc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     """mean over the spatial positions of x [n, C, h, w] (channels-last memory), then y = W * pooled + b in fp32:
     the AvgPool2d(7x7) + Linear tail of TemporalNet (track_to_segment_head.py:17-19,31-35).  weight [out, C], bias [out]."""

@@ -143,3 +143,66 @@ def test_prediction_head_bf16_grouped_tcgen05_launches(cuda_device):
     ref = head16.float().forward_levels([t.float() for t in xd])
     for k in HEAD_KEYS:
         assert rel_err(got[k].cpu().numpy(), ref[k].cpu().numpy()) <= 1e-2, (k, rel_err(got[k].cpu().numpy(), ref[k].cpu().numpy()))
+
+
+# ------------------------------------------------------------------------------------------
+# batched, sync-free candidate generation + cross-class fast NMS
+# ------------------------------------------------------------------------------------------
+def _to_center(b):
+    return np.concatenate([(b[:, 2:] + b[:, :2]) / 2, b[:, 2:] - b[:, :2]], 1)
+
+
+def test_detect_fast_nms_matches_the_reference_detections(cuda_device):
+    """The reference's own post-NMS detections (tests/golden/detections.npz: its FeatureAlign head -> generate_candidate
+    filter -> Detect_TF.cc_fast_nms) from the device kernel: same priors, classes and scores, in the same order."""
+    from stmask_b200 import ops
+    z = load_golden("detections.npz")
+    logits = torch.from_numpy(z["logits"])[0]                                   # [41, h, w]
+    c, h, w = logits.shape
+    conf = torch.softmax(logits.reshape(c, h * w).t(), -1)[None].to(cuda_device)             # [1, P, 41]
+    pri = torch.from_numpy(_to_center(z["boxes"])).to(cuda_device)               # decode(loc = 0, prior) == the recorded boxes
+    loc = torch.zeros(1, h * w, 4, device=cuda_device)
+    ctr = torch.from_numpy(z["centerness"]).reshape(1, -1).to(cuda_device)
+    count, index, cls, score, box = ops.detect_fast_nms(conf, loc, ctr, pri, conf_thresh=0.05, nms_thresh=0.5, top_k=200)
+    n = int(count[0])
+    assert n == len(z["det_prior"])
+    assert index[0, :n].cpu().tolist() == z["det_prior"].tolist()
+    assert cls[0, :n].cpu().tolist() == z["det_class"].tolist()
+    assert np.abs(score[0, :n].cpu().numpy() - z["det_score"]).max() <= 1e-6
+    assert np.abs(box[0, :n].cpu().numpy() - z["boxes"][z["det_prior"]]).max() <= 1e-5
+
+
+def test_detect_fast_nms_batched_full_size_vs_restatement(cuda_device):
+    """4 frames x 15 345 priors x 41 classes (a 384x640 frame's P3..P7 with 3 anchors) in ONE launch against the
+    restatement of the reference's filter + NMS (conftest.detections_after_fast_nms, pinned to the reference in test_oracle.py)."""
+    from conftest import detections_after_fast_nms
+    from stmask_b200 import ops
+    from stmask_b200.prediction_head import make_priors
+    g = torch.Generator().manual_seed(17)
+    pri = torch.cat([make_priors(hh, ww) for hh, ww in ((48, 80), (24, 40), (12, 20), (6, 10), (3, 5))], 1)[0]
+    P = pri.shape[0]
+    assert P == 15345
+    F = 4
+    logits = torch.randn(F, P, 41, generator=g) * 2.0
+    logits[:, :, 0] += 3.0                                                    # mostly background, a few hundred candidates
+    conf = torch.softmax(logits, -1)
+    loc = torch.randn(F, P, 4, generator=g) * 0.5
+    ctr = torch.rand(F, P, generator=g)
+    from stmask_b200 import _lib
+    n0 = _lib.launch_count()
+    count, index, cls, score, box = ops.detect_fast_nms(conf.to(cuda_device), loc.to(cuda_device), ctr.to(cuda_device), pri.to(cuda_device),
+                                                         conf_thresh=0.05, nms_thresh=0.5, top_k=200)
+    assert _lib.launch_count() - n0 == 1
+    for f in range(F):
+        # reference decode (box_utils.py:238-283)
+        b = torch.cat([pri[:, :2] + loc[f, :, :2] * 0.1 * pri[:, 2:], pri[:, 2:] * torch.exp(loc[f, :, 2:] * 0.2)], 1)
+        b[:, :2] -= b[:, 2:] / 2
+        b[:, 2:] += b[:, :2]
+        # the restatement takes [C, h, w] logits of one level; feed it log-probabilities laid out as a 1 x P "map"
+        p_ref, c_ref, s_ref = detections_after_fast_nms(torch.log(conf[f]).t().reshape(41, 1, P), b, ctr[f])
+        n = int(count[f])
+        assert n == len(p_ref) and n > 20, (f, n, len(p_ref))
+        assert index[f, :n].cpu().tolist() == p_ref.tolist()
+        assert cls[f, :n].cpu().tolist() == c_ref.tolist()
+        assert np.abs(score[f, :n].cpu().numpy() - s_ref).max() <= 1e-5
+        assert np.abs(box[f, :n].cpu().numpy() - b[p_ref].numpy()).max() <= 1e-5
