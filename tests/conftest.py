@@ -39,6 +39,9 @@ def cuda_device():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    # torch-side fp32 reference math in the tests (F.conv2d, matmul) must be real fp32, whatever the test order
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     return torch.device("cuda:0")
 
 
