@@ -399,7 +399,7 @@ def deform_conv2d_backend(x_shape: Sequence[int], spec: ConvSpec, dtype: torch.d
 
 
 def deform_conv2d_variant(x_shapes: Sequence[Sequence[int]], spec: ConvSpec, dtype: torch.dtype, backend: str = "auto",
-                          hint: int = 0, device=None, zero_offset: bool = False) -> str:
+                          hint: int = 0, device=None, zero_offset: bool = False, fcb: bool = False) -> str:
     """The kernel instantiation a launch over feature maps of these shapes would run on `device`
     (e.g. 'tcgen05 rows=256 n=256 producer_warps=16 stages=2 pair=1 ...') — shape-only query."""
     n = len(x_shapes)
@@ -411,7 +411,8 @@ def deform_conv2d_variant(x_shapes: Sequence[Sequence[int]], spec: ConvSpec, dty
         p.x_stride_w, p.x_stride_h, p.x_stride_n = spec.in_c, spec.in_c * w, spec.in_c * w * h
         p.y_stride_w, p.y_stride_h, p.y_stride_n = spec.out_c, spec.out_c * wo, spec.out_c * wo * ho
     dt = L.STM_F32 if dtype == torch.float32 else L.STM_BF16
-    conv = spec.c_struct(dt, L.STM_F32, int(hint) | (L.DCN_ZERO_OFFSET if zero_offset else 0), _BACKENDS[backend])
+    conv = spec.c_struct(dt, L.STM_F32, int(hint) | (L.DCN_ZERO_OFFSET if zero_offset else 0) | (L.DCN_FCB_ADA if fcb else 0),
+                         _BACKENDS[backend])
     buf = C.create_string_buffer(256)
     import contextlib
     ctx = torch.cuda.device(device if device is not None else torch.cuda.current_device()) if torch.cuda.is_available() \

@@ -5,7 +5,10 @@ print("workload:", d["config"]["workload"][:150], "| frames/step", d["config"]["
 for k in ("roofline", "roofline_correlation"):
     r = d.get(k)
     if r:
-        print("%s: %s\n   ms %.4f achieved %.1f %s frac %.3f traffic %s" % (k, r["kernel"], r["ms_per_launch"], r["achieved"], r["unit"], r["frac"], r.get("traffic")))
+        print("%s: %s\n   ms %.4f achieved %.1f %s peak %.1f frac %.3f traffic %s %s" % (k, r["kernel"], r["ms_per_launch"], r["achieved"], r["unit"], r["peak"], r["frac"], r.get("traffic"), r.get("regime", "")))
+        if r.get("burst_probe"):
+            b = r["burst_probe"]
+            print("   burst probe: %d frames ms %.4f achieved %.1f frac %.3f clocks %s" % (b["frames"], b["ms_per_launch"], b["achieved"], b["frac"], b["clocks"].get("sm_mhz")))
 for k in ("sustained", "clip_sharding", "frame_sharding"):
     if d.get(k):
         print(k, {a: b for a, b in d[k].items() if a != "clocks"}, (d[k].get("clocks") or {}))
