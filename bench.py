@@ -311,6 +311,7 @@ def main():
 
     import torch
     from stmask_b200.hotpath import HotPath, HotPathConfig
+    torch.set_grad_enabled(False)            # inference benchmark: the operators are forward-only and say so loudly
 
     hp_cfg = HotPathConfig(backbone=args.backbone, fcb=None if args.fcb == "none" else args.fcb,
                            dtype=torch.bfloat16 if args.dtype == "bf16" else torch.float32, backend=args.backend)
