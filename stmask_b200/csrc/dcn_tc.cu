@@ -78,8 +78,8 @@ struct SmemLayout {
   __host__ __device__ SmemLayout(int block_n, int stages, bool pair, int fcb_floats = 0) {
     stage_bytes = M_TILES * A_TILE_BYTES + (pair ? block_n / 2 : block_n) * 128;
     int off = stages * stage_bytes;
-    meta_p = off; off += META_BUFS * ROWS * 32;    // four 64-bit corner pointers per row
-    meta_w = off; off += META_BUFS * ROWS * 8;     // four bf16 corner weights per row
+    meta_p = off; off += META_BUFS * ROWS * 16;    // per row: top-left corner pointer + 2 flag bits, four bf16 corner weights
+    meta_w = off;
     bars = off;   off += (2 * MAX_STAGES + 2) * 8;
     fcb_w = off;  off += (fcb_floats * 4 + 15) & ~15;
     total = off + 1024;   // slack for manual 1024-byte alignment of the base
@@ -202,8 +202,9 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     const int row0 = warp * 4 + (lane >> 3);       // this thread's row in pass 0; pass j adds j * ROWS_PER_PASS
     // 128B swizzle: chunk v of row r goes to chunk v ^ (r & 7); r & 7 is the same in every pass
     const uint32_t dst_off = (uint32_t)(row0 * 128 + ((v ^ (row0 & 7)) << 4));
-    const uint32_t mp_addr = smem_u32(smem + L.meta_p) + (uint32_t)row0 * 32u;
-    const uint32_t mw_addr = smem_u32(smem + L.meta_w) + (uint32_t)row0 * 8u;
+    const uint32_t mp_addr = smem_u32(smem + L.meta_p) + (uint32_t)row0 * 16u;
+    // byte steps to the right column / the lower row of an NHWC map (the same for every sample of this feature map)
+    const uint32_t step_x = (uint32_t)(pr.x_sw * 2), step_y = (uint32_t)(pr.x_sh * 2);
 
     // ---- sample metadata: thread -> (row, CPT of its 4 corners) ----
     const int mrow = tid % ROWS, cg = tid / ROWS;
@@ -291,44 +292,37 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
           const int yy = hb + ti * p.dh, xx = wb + tj * p.dw;
           const bool ok = rvalid && yy >= 0 && yy < pr.in_h && xx >= 0 && xx < pr.in_w;
           const uint64_t ptr = ok ? reinterpret_cast<uint64_t>(ximg + ((int64_t)yy * pr.x_sh + (int64_t)xx * pr.x_sw + g_ * cpd)) : zero_page;
-          *reinterpret_cast<uint2*>(smem + L.meta_p + (buf * ROWS + mrow) * 32) = make_uint2((uint32_t)ptr, (uint32_t)(ptr >> 32));
+          *reinterpret_cast<uint2*>(smem + L.meta_p + (buf * ROWS + mrow) * 16) = make_uint2((uint32_t)ptr, (uint32_t)(ptr >> 32));
         }
         return;
       }
+      // ---- compact 16-byte record per row: base pointer of the top-left corner (clamped into the map) with two flag
+      //      bits in its low bits (bit 0: the right column is a different pixel, bit 1: the lower row is), and the
+      //      four bf16 corner weights.  Corners that carry no weight (outside the map / outside the sample's support /
+      //      rows past the end) keep weight 0 and read a clamped in-map address, so the gather stays branch-free
+      //      and every load is in bounds; one LDS.128 per gather task instead of 40 bytes in three loads (the shared-
+      //      memory / L1 data pipe is this kernel's busiest unit: profiles/r02_dcn_fcb35_pair2.txt). ----
+      if (cg != 0) return;
       const float h = (float)(hb + ti * p.dh) + oy;
       const float w = (float)(wb + tj * p.dw) + ox;
       const bool inside = rvalid && h > -1.f && w > -1.f && h < (float)pr.in_h && w < (float)pr.in_w;
       const float hf = floorf(h), wf = floorf(w);
-      const int h0 = (int)hf, w0 = (int)wf;
       const float lh = h - hf, lw = w - wf;
+      // clamp before the float -> int conversion (huge offsets must not overflow the index arithmetic)
+      const int h0 = (int)fminf(fmaxf(hf, -1.f), (float)pr.in_h), w0 = (int)fminf(fmaxf(wf, -1.f), (float)pr.in_w);
       const float scale = mask_sig ? sigmoidf_(mk) : mk;
-      uint64_t ptr[CPT];
-      uint32_t wt[CPT];
-#pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        const int c = cg * CPT + i;                       // corner: bit 1 = lower row, bit 0 = right column
-        const int yy = h0 + (c >> 1), xx = w0 + (c & 1);
-        const float wy = (c >> 1) ? lh : 1.f - lh, wx = (c & 1) ? lw : 1.f - lw;
-        const bool ok = inside && yy >= 0 && yy < pr.in_h && xx >= 0 && xx < pr.in_w;
-        uint32_t wb16 = ok ? (pack_bf16(wy * wx * scale, 0.f) & 0xffffu) : 0u;
-        const bool live = (wb16 & 0x7fffu) != 0u;
-        if (!live) wb16 = 0u;
-        ptr[i] = live ? reinterpret_cast<uint64_t>(ximg + ((int64_t)yy * pr.x_sh + (int64_t)xx * pr.x_sw + g_ * cpd)) : zero_page;
-        wt[i] = wb16;
-      }
-      uint8_t* mpd = smem + L.meta_p + ((buf * ROWS + mrow) * 32 + cg * CPT * 8);
-      uint8_t* mwd = smem + L.meta_w + ((buf * ROWS + mrow) * 8 + cg * CPT * 2);
-      if (CPT == 4) {
-        reinterpret_cast<uint4*>(mpd)[0] = make_uint4((uint32_t)ptr[0], (uint32_t)(ptr[0] >> 32), (uint32_t)ptr[1 % CPT], (uint32_t)(ptr[1 % CPT] >> 32));
-        reinterpret_cast<uint4*>(mpd)[1] = make_uint4((uint32_t)ptr[2 % CPT], (uint32_t)(ptr[2 % CPT] >> 32), (uint32_t)ptr[3 % CPT], (uint32_t)(ptr[3 % CPT] >> 32));
-        *reinterpret_cast<uint2*>(mwd) = make_uint2(wt[0] | (wt[1 % CPT] << 16), wt[2 % CPT] | (wt[3 % CPT] << 16));
-      } else if (CPT == 2) {
-        *reinterpret_cast<uint4*>(mpd) = make_uint4((uint32_t)ptr[0], (uint32_t)(ptr[0] >> 32), (uint32_t)ptr[1 % CPT], (uint32_t)(ptr[1 % CPT] >> 32));
-        *reinterpret_cast<uint32_t*>(mwd) = wt[0] | (wt[1 % CPT] << 16);
-      } else {
-        *reinterpret_cast<uint2*>(mpd) = make_uint2((uint32_t)ptr[0], (uint32_t)(ptr[0] >> 32));
-        *reinterpret_cast<uint16_t*>(mwd) = (uint16_t)wt[0];
-      }
+      const bool y0ok = inside && h0 >= 0 && h0 < pr.in_h, y1ok = inside && h0 + 1 >= 0 && h0 + 1 < pr.in_h;
+      const bool x0ok = inside && w0 >= 0 && w0 < pr.in_w, x1ok = inside && w0 + 1 >= 0 && w0 + 1 < pr.in_w;
+      const int y0c = min(max(h0, 0), pr.in_h - 1), y1c = min(max(h0 + 1, 0), pr.in_h - 1);
+      const int x0c = min(max(w0, 0), pr.in_w - 1), x1c = min(max(w0 + 1, 0), pr.in_w - 1);
+      const uint32_t w00 = (y0ok && x0ok) ? (pack_bf16((1.f - lh) * (1.f - lw) * scale, 0.f) & 0xffffu) : 0u;
+      const uint32_t w01 = (y0ok && x1ok) ? (pack_bf16((1.f - lh) * lw * scale, 0.f) & 0xffffu) : 0u;
+      const uint32_t w10 = (y1ok && x0ok) ? (pack_bf16(lh * (1.f - lw) * scale, 0.f) & 0xffffu) : 0u;
+      const uint32_t w11 = (y1ok && x1ok) ? (pack_bf16(lh * lw * scale, 0.f) & 0xffffu) : 0u;
+      const uint64_t base = reinterpret_cast<uint64_t>(ximg + ((int64_t)y0c * pr.x_sh + (int64_t)x0c * pr.x_sw + g_ * cpd)) |
+                            (uint64_t)((x1c != x0c ? 1 : 0) | (y1c != y0c ? 2 : 0));
+      *reinterpret_cast<uint4*>(smem + L.meta_p + (buf * ROWS + mrow) * 16) =
+          make_uint4((uint32_t)base, (uint32_t)(base >> 32), w00 | (w01 << 16), w10 | (w11 << 16));
     };
 
     // One gather task = (row, 8 channels) of one K block: 4 corner loads, fp32 blend (FHFMA.BF16: bf16 data and
@@ -339,28 +333,29 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       uint4 c[NC];
     };
     struct GMeta {
-      uint4 p01, p23;
-      uint2 w;
+      uint4 r;             // base pointer lo / hi (flags in the low bits), w0 | w1 << 16, w2 | w3 << 16
     };
     auto read_meta = [&](GMeta& m, int buf, int j) {
-      const uint32_t pa = mp_addr + (uint32_t)((buf * ROWS + j * ROWS_PER_PASS) * 32);
+      const uint32_t pa = mp_addr + (uint32_t)((buf * ROWS + j * ROWS_PER_PASS) * 16);
       if (PLAIN) {
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(m.p01.x), "=r"(m.p01.y) : "r"(pa));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(m.r.x), "=r"(m.r.y) : "r"(pa));
         return;
       }
-      const uint32_t wa = mw_addr + (uint32_t)((buf * ROWS + j * ROWS_PER_PASS) * 8);
-      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m.p01.x), "=r"(m.p01.y), "=r"(m.p01.z), "=r"(m.p01.w) : "r"(pa));
-      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m.p23.x), "=r"(m.p23.y), "=r"(m.p23.z), "=r"(m.p23.w) : "r"(pa + 16u));
-      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(m.w.x), "=r"(m.w.y) : "r"(wa));
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m.r.x), "=r"(m.r.y), "=r"(m.r.z), "=r"(m.r.w) : "r"(pa));
     };
     auto issue = [&](GTask& t, const GMeta& m, uint32_t coff) {
-      t.c[0] = ldg_nc_v4(add_wide(m.p01.x, m.p01.y, coff));
-      if (!PLAIN) {
-        t.w01 = m.w.x; t.w23 = m.w.y;
-        t.c[1 % NC] = ldg_nc_v4(add_wide(m.p01.z, m.p01.w, coff));
-        t.c[2 % NC] = ldg_nc_v4(add_wide(m.p23.x, m.p23.y, coff));
-        t.c[3 % NC] = ldg_nc_v4(add_wide(m.p23.z, m.p23.w, coff));
+      if (PLAIN) {
+        t.c[0] = ldg_nc_v4(add_wide(m.r.x, m.r.y, coff));
+        return;
       }
+      t.w01 = m.r.z; t.w23 = m.r.w;
+      const uint32_t dx = (m.r.x & 1u) ? step_x : 0u, dy = (m.r.x & 2u) ? step_y : 0u;
+      const uint64_t p00 = add_wide(m.r.x & ~3u, m.r.y, coff);
+      const uint64_t p10 = p00 + dy;
+      t.c[0] = ldg_nc_v4(p00);
+      t.c[1 % NC] = ldg_nc_v4(p00 + dx);
+      t.c[2 % NC] = ldg_nc_v4(p10);
+      t.c[3 % NC] = ldg_nc_v4(p10 + dx);
     };
     auto finish = [&](const GTask& t, uint32_t dst) {
       uint32_t o[4];
