@@ -425,7 +425,7 @@ def main():
         # Which measured peak applies: MEASURED_PEAKS.json gives the cuBLAS bf16 rate as a burst (a kernel timed alone at
         # full clocks) and sustained under the 1 kW power cap.  A launch over all this rank's frames runs for many ms and,
         # repeated back to back, drives the GPU into the power cap (sw_power_cap, SM clock well below max): that is the
-        # sustained regime.  The same launch over 72 frames (~1 ms) stays at full clocks: reported as `burst_probe`.
+        # sustained regime.  The same launch over 74 frames (~1 ms) stays at full clocks: reported as `burst_probe`.
         capped = "sw_power_cap" in (kc.get("reasons") or []) or (kc.get("sm_mhz") and kc.get("sm_max_mhz") and kc["sm_mhz"] < 0.95 * kc["sm_max_mhz"])
         peak = peaks["bf16_sustained"] if capped else peaks["bf16_burst"]
         roof = {"kernel": f"deform_conv2d FCB 3x5 256->256, P3..P7, {n_local} frames, one launch [{variant}]", "bound": "tensor",
@@ -435,7 +435,8 @@ def main():
                 "clocks_during_launches": kc, "frac_of_burst_peak": ach / peaks["bf16_burst"],
                 "frac_of_sustained_peak": ach / peaks["bf16_sustained"],
                 "peak_source": peaks["src"] + (", sustained" if capped else ", burst")}
-        nb = min(72, n_local)
+        # 74 frames: 2958 CTAs = 9.99 waves of the 296 CTAs resident on 148 SMs (72 frames leave a 0.72-full last wave)
+        nb = min(74, n_local)
         if nb < n_local:
             xb, ob, yb = [x[:nb] for x in xs], [o[:nb] for o in boxes], [y[:nb] for y in outs]
             time.sleep(0.5)                        # let the clocks recover from the capped stretch above
