@@ -64,6 +64,20 @@ if a.case.startswith("fcb"):
     print(ops.deform_conv2d_variant([tuple(x.shape) for x in xs], spec, torch.bfloat16, a.backend, a.hint))
     timeit(lambda: ops.deform_conv2d_multi(xs, offs, None, wp, None, spec, relu=True, backend=a.backend, outs=outs, hint=a.hint),
            flops=2.0 * F * px * 256 * 256 * kh * kw)
+elif a.case.startswith("fused"):      # FCB with the offsets derived inside the kernel from the box deltas (what the step launches)
+    kh, kw = {"fused33": (3, 3), "fused35": (3, 5), "fused53": (5, 3)}[a.case]
+    spec = ops.ConvSpec(256, 256, (kh, kw), 1, ((kh - 1) // 2, (kw - 1) // 2))
+    w = (torch.randn(256, 256, kh, kw, device=dev) / (256 * kh * kw) ** 0.5).bfloat16()
+    wp = ops.pack_weight(w, spec, torch.bfloat16)
+    lv = fpn_level_sizes()
+    xs = [torch.randn(F, 256, h, ww, device=dev).bfloat16().contiguous(memory_format=torch.channels_last) for h, ww in lv]
+    deltas = [torch.randn(F, 4, h, ww, device=dev) for h, ww in lv]
+    w_off = torch.randn(2 * kh * kw, 4, 1, 1, device=dev) * 0.5
+    outs = ops.deform_conv2d_fcb_multi(xs, deltas, wp, spec, w_off, relu=True, hint=a.hint)
+    px = sum(h * ww for h, ww in lv)
+    print(ops.deform_conv2d_variant([tuple(x.shape) for x in xs], spec, torch.bfloat16, a.backend, a.hint, fcb=True))
+    timeit(lambda: ops.deform_conv2d_fcb_multi(xs, deltas, wp, spec, w_off, relu=True, outs=outs, hint=a.hint),
+           flops=2.0 * F * px * 256 * 256 * kh * kw)
 elif a.case.startswith("bb"):
     C, H, W, s = {"bb128s2": (128, 96, 160, 2), "bb128": (128, 48, 80, 1), "bb256s2": (256, 48, 80, 2), "bb256": (256, 24, 40, 1),
                   "bb512s2": (512, 24, 40, 2)}[a.case]
@@ -120,7 +134,7 @@ elif a.case == "corrsweep":       # BASELINE.json configs[1]: batch 8 over P3..P
     xs = [(torch.randn(8, 256, h, ww, device=dev).bfloat16().contiguous(memory_format=torch.channels_last),
            torch.randn(8, 256, h, ww, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)) for h, ww in lv]
     px = sum(h * ww for h, ww in lv)
-    fn = lambda: [ops.correlation(p, q, 11, 1, backend=a.backend) for p, q in xs]
+    fn = lambda: ops.correlation_multi([p for p, _ in xs], [q for _, q in xs], 11, 1, scale=1 / 256, leaky_slope=0.1)   # ONE grouped launch
     timeit(fn, nbytes=8 * px * (2 * 256 + 121) * 2.0)
 else:
     raise SystemExit("unknown case")
