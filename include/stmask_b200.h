@@ -15,6 +15,8 @@
  *                              (layers/modules/track_to_segment_head.py:65-88)
  *   stm_detect_fast_nms_fwd <- generate_candidate + Detect_TF.cc_fast_nms, batched and sync-free
  *                              (layers/functions/TF_utils.py:54-82, layers/functions/detection_TF.py:85-134)
+ *   stm_mask_assembly_fwd   <- generate_mask + crop           (layers/mask_utils.py:111-128, layers/box_utils.py:341-364)
+ *   stm_mask_iou_fwd        <- mask_iou                       (layers/box_utils.py:435-447)
  *   stm_pool_fc_fwd         <- TemporalNet's AvgPool2d(7x7) + fc + fc_coeff tail; its three 3x3 convs are
  *                              stm_deform_conv2d_fwd with STM_DCN_ZERO_OFFSET
  *                              (layers/modules/track_to_segment_head.py:10-37)
@@ -287,6 +289,25 @@ int stm_detect_fast_nms_fwd(const float* conf, const float* loc, const float* ce
                             int32_t frames, int32_t n_priors, int32_t n_classes, int32_t top_k,
                             float conf_thresh, float nms_thresh,
                             int32_t* count, int32_t* index, int32_t* cls, float* score, float* box, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Mask assembly and mask IoU for a batch of frames                           */
+/* (generate_mask, layers/mask_utils.py:111-128; crop, box_utils.py:341-364;  */
+/*  mask_iou, box_utils.py:435-447; callers track_TF.py:76-112)               */
+/* ------------------------------------------------------------------------- */
+/* proto [frames, h, w, k] prototypes, coeff [frames, max_n, k] raw mask coefficients (tanh is applied here),
+ * boxes [frames, max_n, 4] relative x1, y1, x2, y2, count [frames] valid detections per frame (NULL: max_n) — float32 /
+ * int32, contiguous.  masks [frames, max_n, h, w] = sigmoid(proto . tanh(coeff)) inside the box grown by one pixel
+ * (the reference's crop), 0 outside; mask_bits [frames, max_n, ceil(h*w/32)] = masks > 0.5, one bit per pixel.
+ * Rows past count[f] are left untouched. */
+int stm_mask_assembly_fwd(const float* proto, const float* coeff, const float* boxes, const int32_t* count,
+                          float* masks, uint32_t* mask_bits, int32_t frames, int32_t h, int32_t w, int32_t k,
+                          int32_t max_n, void* stream);
+
+/* iou[f, i, j] = |A_i and B_j| / |A_i or B_j| (0 for an empty union) on the bit masks above:
+ * bits_a [frames, max_a, words], bits_b [frames, max_b, words], count_a / count_b [frames] or NULL, iou [frames, max_a, max_b]. */
+int stm_mask_iou_fwd(const uint32_t* bits_a, const uint32_t* bits_b, const int32_t* count_a, const int32_t* count_b,
+                     float* iou, int32_t frames, int32_t max_a, int32_t max_b, int32_t words, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* TemporalNet tail: y[n, :] = W * mean over the hw pixels of x[n] + b        */

@@ -22,6 +22,7 @@ Sources of truth:
                         the correlate / concat / RoIAlign / TemporalNet call sites of CandidateShift and the shifted boxes
   prediction_head.npz   the reference's own PredictionModule_FC.forward (R101 FCA+FCB(ada) head, shared over five levels):
                         loc / centerness / conf / mask_coeff / track / priors, weights rebuilt from the recorded seed
+  mask_assembly.npz     the reference's own generate_mask / crop / mask_iou (mask_utils.py:111-128, box_utils.py:341-364,435-447)
   temporal_net.npz      the reference's own TemporalNet.forward + bbox_feat_extractor (track_to_segment_head.py:10-37,
                         65-88) on a 633-channel concat; the 40 MB of weights are rebuilt from the recorded seed
                         (default nn init in construction order) and pinned by per-parameter checksums
@@ -326,6 +327,34 @@ def _prediction_head():
                         **{f"x{i}": x.numpy() for i, x in enumerate(xs)}, **res)
 
 
+def _mask_assembly():
+    """The reference's own generate_mask (mask_utils.py:111-128: tanh coefficients, sigmoid, crop with 1 px padding) and
+    mask_iou (box_utils.py:435-447) on two sets of detections over one prototype map."""
+    from . import ref_model
+    ref_model._install_stubs()
+    import STMask  # noqa: F401
+    from datasets.config import set_cfg
+    set_cfg("STMask_plus_base_ada_config")
+    import layers.mask_utils as mu
+    import layers.box_utils as bu
+    g = torch.Generator().manual_seed(21)
+    proto = torch.relu(torch.randn(24, 40, 32, generator=g))
+    out = {"proto": proto.numpy()}
+    masks = []
+    for name, n in (("a", 9), ("b", 6)):
+        coeff = torch.randn(n, 32, generator=g)
+        c = torch.rand(n, 2, generator=g)
+        wh = 0.08 + torch.rand(n, 2, generator=g) * 0.4
+        boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
+        boxes[0] = torch.tensor([0.9, 0.2, 0.3, 0.7])            # x1 > x2: sanitize swaps them
+        boxes[1] = torch.tensor([-0.2, -0.1, 1.3, 1.2])          # larger than the frame: clamped
+        m = mu.generate_mask(proto, coeff, boxes)
+        masks.append(m)
+        out[f"{name}.coeff"], out[f"{name}.boxes"], out[f"{name}.masks"] = coeff.numpy(), boxes.numpy(), m.numpy()
+    out["iou"] = bu.mask_iou(masks[0].gt(0.5).float(), masks[1].gt(0.5).float()).numpy()
+    np.savez_compressed(os.path.join(OUT, "mask_assembly.npz"), **out)
+
+
 def _model_r50():
     """BASELINE.json configs[0] / SURVEY.md 8(c) "Model:" known answer: the reference's own STMask (R50-DCN-FPN
     FCA+TF) on a synthetic 2-frame clip through oracle/ref_model.py; every hot-op call site of frame 2."""
@@ -351,6 +380,7 @@ def main():
     _temporal_net()
     _model_r50()
     _prediction_head()
+    _mask_assembly()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

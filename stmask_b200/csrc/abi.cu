@@ -357,6 +357,27 @@ int stm_detect_fast_nms_fwd(const float* conf, const float* loc, const float* ce
                            cls, score, box, (cudaStream_t)stream);
 }
 
+int stm_mask_assembly_fwd(const float* proto, const float* coeff, const float* boxes, const int32_t* count, float* masks,
+                          uint32_t* mask_bits, int32_t frames, int32_t h, int32_t w, int32_t k, int32_t max_n, void* stream) {
+  clear_error();
+  STM_CHECK_ARG(frames >= 0 && h > 0 && w > 0 && max_n >= 0, "bad size");
+  STM_CHECK_ARG(k > 0 && k <= 64, "at most 64 prototypes (got %d)", k);
+  STM_CHECK_ARG(max_n <= 65535 && frames <= 65535, "too many detections / frames for one launch");
+  if (frames == 0 || max_n == 0) return STM_OK;
+  STM_CHECK_ARG(proto && coeff && boxes && masks && mask_bits, "null pointer");
+  return launch_mask_assembly(proto, coeff, boxes, count, masks, mask_bits, frames, h, w, k, max_n, (cudaStream_t)stream);
+}
+
+int stm_mask_iou_fwd(const uint32_t* bits_a, const uint32_t* bits_b, const int32_t* count_a, const int32_t* count_b, float* iou,
+                     int32_t frames, int32_t max_a, int32_t max_b, int32_t words, void* stream) {
+  clear_error();
+  STM_CHECK_ARG(frames >= 0 && max_a >= 0 && max_b >= 0 && words > 0, "bad size");
+  STM_CHECK_ARG(max_a <= 65535 && frames <= 65535, "too many masks / frames for one launch");
+  if (frames == 0 || max_a == 0 || max_b == 0) return STM_OK;
+  STM_CHECK_ARG(bits_a && bits_b && iou, "null pointer");
+  return launch_mask_iou(bits_a, bits_b, count_a, count_b, iou, frames, max_a, max_b, words, (cudaStream_t)stream);
+}
+
 int stm_roi_align_fwd(const StmRoiAlignDesc* d, const void* feat, const float* rois, void* out, void* stream) {
   clear_error();
   STM_CHECK_ARG(d != nullptr, "roi_align descriptor is null");

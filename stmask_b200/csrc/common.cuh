@@ -138,6 +138,10 @@ int launch_pool_fc(const void* x, int dtype, int n, int hw, int c, int64_t x_str
 int launch_detect_nms(const float* conf, const float* loc, const float* centerness, const float* priors, int frames, int P, int C,
                       int top_k, float conf_thresh, float nms_thresh, int32_t* count, int32_t* index, int32_t* cls, float* score,
                       float* box, cudaStream_t stream);
+int launch_mask_assembly(const float* proto, const float* coeff, const float* boxes, const int32_t* count, float* masks,
+                         uint32_t* bits, int frames, int h, int w, int k, int max_n, cudaStream_t stream);
+int launch_mask_iou(const uint32_t* a, const uint32_t* b, const int32_t* na, const int32_t* nb, float* iou, int frames, int max_a,
+                    int max_b, int words, cudaStream_t stream);
 int launch_roi_align(const StmRoiAlignDesc& d, const void* feat, const float* rois, void* out, cudaStream_t stream);
 
 }  // namespace stm

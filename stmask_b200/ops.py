@@ -860,6 +860,42 @@ def detect_fast_nms(conf: torch.Tensor, loc: torch.Tensor, centerness: Optional[
     return count, index, cls, score, box
 
 
+def mask_assembly(proto: torch.Tensor, coeff: torch.Tensor, boxes: torch.Tensor, count: Optional[torch.Tensor] = None):
+    """generate_mask + crop for a batch of frames (mask_utils.py:111-128, box_utils.py:341-364): proto [F, h, w, k],
+    coeff [F, n, k] (raw; tanh applied inside), boxes [F, n, 4] relative xyxy, count [F] int32 or None.
+    Returns (masks [F, n, h, w] float32, mask_bits [F, n, ceil(h*w/32)] int32: masks > 0.5 as bit planes)."""
+    _require_cuda(proto, "proto")
+    if proto.dim() != 4 or coeff.dim() != 3 or boxes.shape != coeff.shape[:2] + (4,) or coeff.shape[2] != proto.shape[3]:
+        raise ValueError("proto [F, h, w, k], coeff [F, n, k], boxes [F, n, 4] expected")
+    f, h, w, k = proto.shape
+    n = coeff.shape[1]
+    words = (h * w + 31) // 32
+    pr, cf, bx = proto.float().contiguous(), coeff.float().contiguous(), boxes.float().contiguous()
+    masks = torch.zeros((f, n, h, w), dtype=torch.float32, device=proto.device)
+    bits = torch.zeros((f, n, words), dtype=torch.int32, device=proto.device)
+    with torch.cuda.device(proto.device):
+        L.check(L.lib().stm_mask_assembly_fwd(pr.data_ptr(), cf.data_ptr(), bx.data_ptr(), count.data_ptr() if count is not None else None,
+                                              masks.data_ptr(), bits.data_ptr(), f, h, w, k, n, _stream(proto)), "stm_mask_assembly_fwd")
+    return masks, bits
+
+
+def mask_iou_bits(bits_a: torch.Tensor, bits_b: torch.Tensor, count_a: Optional[torch.Tensor] = None,
+                  count_b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mask_iou (box_utils.py:435-447) on bit-plane masks from `mask_assembly`: [F, na, words] x [F, nb, words] -> [F, na, nb]."""
+    _require_cuda(bits_a, "bits_a")
+    if bits_a.dim() != 3 or bits_b.dim() != 3 or bits_a.shape[0] != bits_b.shape[0] or bits_a.shape[2] != bits_b.shape[2]:
+        raise ValueError("bit masks must be [F, n, words] with equal F and words")
+    a, b = bits_a.contiguous(), bits_b.contiguous()
+    f, na, words = a.shape
+    nb = b.shape[1]
+    iou = torch.zeros((f, na, nb), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        L.check(L.lib().stm_mask_iou_fwd(a.data_ptr(), b.data_ptr(), count_a.data_ptr() if count_a is not None else None,
+                                         count_b.data_ptr() if count_b is not None else None, iou.data_ptr(), f, na, nb, words, _stream(a)),
+                "stm_mask_iou_fwd")
+    return iou
+
+
 def pool_fc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     """mean over the spatial positions of x [n, C, h, w] (channels-last memory), then y = W * pooled + b in fp32:
     the AvgPool2d(7x7) + Linear tail of TemporalNet (track_to_segment_head.py:17-19,31-35).  weight [out, C], bias [out]."""

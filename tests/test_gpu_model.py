@@ -206,3 +206,31 @@ def test_detect_fast_nms_batched_full_size_vs_restatement(cuda_device):
         assert cls[f, :n].cpu().tolist() == c_ref.tolist()
         assert np.abs(score[f, :n].cpu().numpy() - s_ref).max() <= 1e-5
         assert np.abs(box[f, :n].cpu().numpy() - b[p_ref].numpy()).max() <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# mask assembly + mask IoU on the device (the rest of SURVEY.md 8f rank 4 short of the tracker's state machine)
+# ------------------------------------------------------------------------------------------
+def test_mask_assembly_and_mask_iou_vs_reference(cuda_device):
+    from stmask_b200 import ops
+    z = load_golden("mask_assembly.npz")
+    proto = torch.from_numpy(z["proto"]).to(cuda_device)
+    F = 3                                                        # the same frame three times with different valid counts
+    na, nb = z["a.coeff"].shape[0], z["b.coeff"].shape[0]
+    rep = lambda a: torch.from_numpy(a).to(cuda_device)[None].repeat(F, *([1] * a.ndim)).contiguous()
+    cnt_a = torch.tensor([na, na - 2, 0], dtype=torch.int32, device=cuda_device)
+    masks_a, bits_a = ops.mask_assembly(rep(z["proto"]), rep(z["a.coeff"]), rep(z["a.boxes"]), cnt_a)
+    masks_b, bits_b = ops.mask_assembly(rep(z["proto"]), rep(z["b.coeff"]), rep(z["b.boxes"]))
+    assert masks_a.shape == (F, na, 24, 40)
+    assert np.abs(masks_a[0].cpu().numpy() - z["a.masks"]).max() <= 1e-5
+    assert np.abs(masks_b[2].cpu().numpy() - z["b.masks"]).max() <= 1e-5
+    assert np.abs(masks_a[1, :na - 2].cpu().numpy() - z["a.masks"][:na - 2]).max() <= 1e-5
+    assert float(masks_a[1, na - 2:].abs().max()) == 0.0 and float(masks_a[2].abs().max()) == 0.0     # past count[f]: untouched
+    iou = ops.mask_iou_bits(bits_a, bits_b, cnt_a, None)
+    assert np.abs(iou[0].cpu().numpy() - z["iou"]).max() <= 1e-6
+    assert np.abs(iou[1, :na - 2].cpu().numpy() - z["iou"][:na - 2]).max() <= 1e-6 and float(iou[2].abs().max()) == 0.0
+    # the bit planes are the thresholded masks
+    want_bits = (torch.from_numpy(z["a.masks"]) > 0.5).reshape(na, -1)
+    got = bits_a[0].cpu().numpy().view(np.uint32)
+    unpacked = ((got[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None]) & 1).reshape(na, -1)[:, :960].astype(bool)
+    assert np.array_equal(unpacked, want_bits.numpy())
