@@ -97,7 +97,9 @@ enum {
    * tensor but the regressed box deltas [batch, 4 = (t_x, t_y, t_w, t_h), out_h, out_w] (strides off_stride_*,
    * dtype conv->offset_dtype); every tap's (dy, dx) is derived inside the sampling kernel. */
   STM_DCN_FCB_ADA = 1024,       /* offsets = 1x1 conv_offset(deltas)            (Featurealign.py:20-25,44)   */
-  STM_DCN_FCB_ALI = 2048        /* offsets = closed form of the box transform   (Featurealign.py:46-69)      */
+  STM_DCN_FCB_ALI = 2048,       /* offsets = closed form of the box transform   (Featurealign.py:46-69)      */
+  STM_DCN_HINT_GATHER = 4096    /* STM_DCN_ZERO_OFFSET only: keep the plain convolution on the gather main loop instead of
+                                   the TMA shifted-view kernel (tests compare the two)                         */
 };
 
 /* Parameters shared by every problem of one call (one weight tensor). */

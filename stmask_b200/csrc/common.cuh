@@ -125,6 +125,10 @@ bool dcn_tc_supported(const StmDcnConv* conv, const StmDcnProblem* probs, int n,
 bool dcn_tc_shape_supported(const StmDcnConv* conv, const StmDcnProblem* probs, int n, const char** why);
 size_t dcn_tc_workspace(const StmDcnConv* conv, const StmDcnProblem* probs, int n);
 int dcn_tc_variant(const StmDcnConv* conv, const DcnParams& p, char* buf, size_t len);
+// plain convolution with TMA-loaded, shifted-view A operands (conv_tma.cu)
+bool conv_tma_shape_supported(const StmDcnConv* conv, const DcnParams& p, const char** why);
+int conv_tma_variant(const StmDcnConv* conv, const DcnParams& p, char* buf, size_t len);
+int launch_conv_tma(const StmDcnConv* conv, const DcnParams& p, cudaStream_t stream);
 
 int launch_corr_simt(const StmCorrDesc& d, const void* x1, const void* x2, const void* fa, const void* fb, void* out,
                      cudaStream_t stream);

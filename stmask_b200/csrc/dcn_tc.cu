@@ -722,6 +722,8 @@ bool dcn_tc_shape_supported(const StmDcnConv* c, const StmDcnProblem* pr, int n,
 size_t dcn_tc_workspace(const StmDcnConv*, const StmDcnProblem*, int) { return 0; }
 
 int dcn_tc_variant(const StmDcnConv* conv, const DcnParams& p, char* buf, size_t len) {
+  const char* why = "";
+  if (conv_tma_shape_supported(conv, p, &why)) return conv_tma_variant(conv, p, buf, len);
   TcPlan pl;
   const int rc = make_plan(conv, p, &pl);
   if (rc != STM_OK) return rc;
@@ -739,6 +741,11 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   p.flags &= 0xffff;
   if (pl_fcb_needs_weight(p) && p.fcb_w == nullptr) { set_error("FCB(ada) needs the conv_offset weight"); return STM_ERR_INVALID_ARGUMENT; }
   if (conv->offset_dtype == STM_BF16) p.flags |= FLAG_OFFSETS_BF16;
+  {
+    // regular convolutions that tile well: A operand by TMA, taps as shifted descriptor views (no gather at all)
+    const char* why = "";
+    if (conv_tma_shape_supported(conv, p_in, &why)) return launch_conv_tma(conv, p_in, stream);
+  }
   TcPlan pl;
   const int prc = make_plan(conv, p, &pl);
   if (prc != STM_OK) return prc;

@@ -199,7 +199,14 @@ def test_launch_plan_is_a_pure_function_of_the_call():
     c128 = ops.deform_conv2d_variant([(72, 128, 48, 80)], ops.ConvSpec(128, 128, 3, 1, 1), torch.bfloat16)
     assert "rows=128 n=128" in c128 and "ctas_per_sm=2" in c128, c128
     pred = ops.deform_conv2d_variant([(72, 256, 24, 40)], ops.ConvSpec(256, 32, 3, 1, 1), torch.bfloat16, zero_offset=True)
-    assert "plain=1" in pred and "n=32" in pred, pred
+    assert "plain=1" in pred and "n=32" in pred and "tma-conv stride=1" in pred and "resident=1" in pred, pred
+    pred2 = ops.deform_conv2d_variant([(72, 512, 24, 40)], ops.ConvSpec(512, 32, 3, 2, 1), torch.bfloat16, zero_offset=True)
+    assert "tma-conv stride=2" in pred2 and "resident=0" in pred2, pred2          # 72 weight slices: a ring, not resident
+    gath = ops.deform_conv2d_variant([(72, 256, 24, 40)], ops.ConvSpec(256, 32, 3, 1, 1), torch.bfloat16, zero_offset=True,
+                                     hint=_lib.DCN_HINT_GATHER)
+    assert "tma-conv" not in gath and "plain=1" in gath, gath
+    crops = ops.deform_conv2d_variant([(1500, 640, 7, 7)], ops.ConvSpec(640, 512, 3, 1, 1), torch.bfloat16, zero_offset=True)
+    assert "tma-conv" not in crops, crops                            # 7x7 crops leave 62 % of a shifted-view tile dead: gather loop
     for k in ("STM_DCN_MTILES", "STM_DCN_PW", "STM_CORR_TW"):          # no hidden global state behind the ABI
         os.environ[k] = "1"
     try:
