@@ -17,6 +17,8 @@
  *                              (layers/functions/TF_utils.py:54-82, layers/functions/detection_TF.py:85-134)
  *   stm_mask_assembly_fwd   <- generate_mask + crop           (layers/mask_utils.py:111-128, layers/box_utils.py:341-364)
  *   stm_mask_iou_fwd        <- mask_iou                       (layers/box_utils.py:435-447)
+ *   stm_track_update_fwd    <- the matching state machine of Track_TF.track + compute_comp_scores, for a batch of clips
+ *                              (layers/functions/track_TF.py:52-181, layers/functions/TF_utils.py:98-123)
  *   stm_pool_fc_fwd         <- TemporalNet's AvgPool2d(7x7) + fc + fc_coeff tail; its three 3x3 convs are
  *                              stm_deform_conv2d_fwd with STM_DCN_ZERO_OFFSET
  *                              (layers/modules/track_to_segment_head.py:10-37)
@@ -52,7 +54,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define STM_ABI_VERSION 5
+#define STM_ABI_VERSION 6
 
 typedef enum StmStatus {
   STM_OK = 0,
@@ -310,6 +312,57 @@ int stm_mask_assembly_fwd(const float* proto, const float* coeff, const float* b
  * bits_a [frames, max_a, words], bits_b [frames, max_b, words], count_a / count_b [frames] or NULL, iou [frames, max_a, max_b]. */
 int stm_mask_iou_fwd(const uint32_t* bits_a, const uint32_t* bits_b, const int32_t* count_a, const int32_t* count_b,
                      float* iou, int32_t frames, int32_t max_a, int32_t max_b, int32_t words, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Tracker state machine for a batch of independent clips                     */
+/* (Track_TF.track, layers/functions/track_TF.py:52-181; compute_comp_scores, */
+/*  layers/functions/TF_utils.py:98-123) — one launch per frame, no host sync */
+/* ------------------------------------------------------------------------- */
+/* The reference's `prev_candidate` dict of growing tensors as fixed-capacity DEVICE arrays owned by the caller
+ * (rows past n_obj[clip] are unused).  `mask` / `centerness` may be NULL. */
+typedef struct StmTrackState {
+  int32_t* n_obj;        /* [clips]            objects tracked so far in each clip (0 = `prev_candidate is None`) */
+  float* box;            /* [clips, cap, 4]    x1, y1, x2, y2 (relative)                                          */
+  float* score;          /* [clips, cap]                                                                          */
+  int32_t* cls;          /* [clips, cap]                                                                          */
+  float* coeff;          /* [clips, cap, k]    mask coefficients                                                  */
+  float* track;          /* [clips, cap, e]    L2-normalised track embeddings                                     */
+  float* centerness;     /* [clips, cap]                                                                          */
+  int32_t* tracked;      /* [clips, cap]       `tracked_mask`: frames since the object was last matched           */
+  uint32_t* mask_bits;   /* [clips, cap, words] masks > 0.5 as bit planes (stm_mask_assembly_fwd)                  */
+  float* mask;           /* [clips, cap, hw]   soft masks                                                         */
+} StmTrackState;
+
+/* This frame's detections after fast NMS, per clip (stm_detect_fast_nms_fwd / stm_mask_assembly_fwd outputs). */
+typedef struct StmTrackDets {
+  const int32_t* count;      /* [clips] valid rows, or NULL: max_det                */
+  const float* box;          /* [clips, max_det, 4]                                 */
+  const float* score;        /* [clips, max_det]                                    */
+  const int32_t* cls;        /* [clips, max_det]                                    */
+  const float* coeff;        /* [clips, max_det, k]                                 */
+  const float* track;        /* [clips, max_det, e]                                 */
+  const float* centerness;   /* [clips, max_det] or NULL                            */
+  const uint32_t* mask_bits; /* [clips, max_det, words]                             */
+  const float* mask;         /* [clips, max_det, hw] or NULL                        */
+} StmTrackDets;
+
+typedef struct StmTrackParams {
+  int32_t clips, cap, max_det;   /* cap, max_det <= 256                                                              */
+  int32_t k, e, words, hw;       /* mask coefficients, embedding size, words per bit plane, pixels per soft mask     */
+  int32_t max_age;               /* an object is reported while tracked <= max_age (10, track_TF.py:160)             */
+  float match_coeff[4];          /* cfg.match_coeff: weights of score, mask IoU, box IoU, same label                 */
+  float bbox_dummy_iou;          /* IoU of the "new object" column (0.3, track_TF.py:126)                            */
+  float conf_thresh;             /* cfg.eval_conf_thresh (track_TF.py:164)                                           */
+} StmTrackParams;
+
+/* One frame of every clip: ages the tracked objects, matches the detections (mask_iou [clips, max_det, cap] =
+ * stm_mask_iou_fwd(det bits, state bits) after the caller's CandidateShift), runs the reference's sequential assignment
+ * in detection order and copies the winning detections' rows into the state.  is_first [clips] (uint8, or NULL) resets a
+ * clip's state (a new video).  Outputs: det_slot [clips, max_det] the state row each detection went to (-1: it lost its
+ * object to a higher-scoring detection, or the state is full), keep [clips, cap] the output filter of track_TF.py:158-165;
+ * an object's id is its row index (box_ids = arange, track_TF.py:158). */
+int stm_track_update_fwd(const StmTrackParams* params, const StmTrackState* state, const StmTrackDets* dets,
+                         const float* mask_iou, const uint8_t* is_first, int32_t* det_slot, uint8_t* keep, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* TemporalNet tail: y[n, :] = W * mean over the hw pixels of x[n] + b        */

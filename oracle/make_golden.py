@@ -22,6 +22,7 @@ Sources of truth:
                         the correlate / concat / RoIAlign / TemporalNet call sites of CandidateShift and the shifted boxes
   prediction_head.npz   the reference's own PredictionModule_FC.forward (R101 FCA+FCB(ada) head, shared over five levels):
                         loc / centerness / conf / mask_coeff / track / priors, weights rebuilt from the recorded seed
+  tracker.npz           the reference's own Track_TF.track on a synthetic 7-frame clip (track_TF.py:52-181), recorded shifts
   mask_assembly.npz     the reference's own generate_mask / crop / mask_iou (mask_utils.py:111-128, box_utils.py:341-364,435-447)
   temporal_net.npz      the reference's own TemporalNet.forward + bbox_feat_extractor (track_to_segment_head.py:10-37,
                         65-88) on a 633-channel concat; the 40 MB of weights are rebuilt from the recorded seed
@@ -355,6 +356,90 @@ def _mask_assembly():
     np.savez_compressed(os.path.join(OUT, "mask_assembly.npz"), **out)
 
 
+TRACK_SEED = 77
+
+
+def _tracker():
+    """The reference's own Track_TF.track (track_TF.py:52-181) on a synthetic 7-frame clip: first frame, matches, two
+    detections competing for one object, new objects, an empty frame (shift only), objects ageing, a video restart.
+    `CandidateShift` is replaced by a recorded, seeded shift built from the reference's own decode / center_size /
+    generate_mask (TF_utils.py:38-49 without the network): the matching state machine is what this fixture pins."""
+    from . import ref_model
+    ref_model._install_stubs()
+    import STMask  # noqa: F401
+    from datasets.config import cfg, set_cfg
+    set_cfg("STMask_plus_base_ada_config")
+    cfg.eval_conf_thresh = 0.3
+    import layers.functions.track_TF as tt
+    import layers.box_utils as bu
+    import layers.mask_utils as mu
+    assert cfg.train_track and list(cfg.match_coeff) == [0, 1, 2, 0]
+    g = torch.Generator().manual_seed(TRACK_SEED)
+    H, W, K, E = 24, 40, 32, 16
+    n_ident = 9
+    ident_emb = torch.nn.functional.normalize(torch.randn(n_ident, E, generator=g), dim=1)
+    ident_c = 0.15 + 0.7 * torch.rand(n_ident, 2, generator=g)
+    ident_wh = 0.12 + 0.2 * torch.rand(n_ident, 2, generator=g)
+    ident_coeff = torch.randn(n_ident, K, generator=g)
+    ident_cls = torch.randint(1, 41, (n_ident,), generator=g)
+    # which identities are detected in each frame (an identity listed twice = two competing detections)
+    frames = [([0, 1, 2, 3], True), ([1, 0, 4, 2, 2], False), ([], False), ([3, 5, 0, 0, 1], False), ([6, 2, 4], False),
+              ([7, 8, 1], True), ([8, 7, 7, 0], False)]
+    shifts, shifted = [], []
+
+    def stub_shift(net, ref_candidate, next_candidate, img=None, img_meta=None, display=False):
+        n = ref_candidate["box"].shape[0]
+        loc = torch.randn(n, 4, generator=g) * 0.3
+        dco = torch.randn(n, K, generator=g) * 0.05
+        shifts.append((loc, dco))
+        out = {k: v.clone() for k, v in next_candidate.items() if k in {"proto", "fpn_feat", "T2S_feat"}}
+        box = bu.decode(loc, bu.center_size(ref_candidate["box"].clone()))
+        coeff = ref_candidate["mask_coeff"].clone() + dco
+        out["box"] = box.clone()
+        out["score"] = ref_candidate["score"].clone() * 0.95
+        out["mask_coeff"] = coeff.clone()
+        out["mask"] = mu.generate_mask(next_candidate["proto"], coeff, box).clone()
+        shifted.append({k: out[k].numpy().copy() for k in ("box", "score", "mask_coeff", "mask")})
+        return out
+
+    tt.CandidateShift = stub_shift
+    tracker = tt.Track_TF()
+    out = {"seed": np.int64(TRACK_SEED), "n_frames": np.int64(len(frames)), "conf_thresh": np.float32(cfg.eval_conf_thresh),
+           "match_coeff": np.asarray(cfg.match_coeff, np.float32)}
+    for f, (ids, first) in enumerate(frames):
+        n = len(ids)
+        idx = torch.tensor(ids, dtype=torch.long)
+        proto = torch.relu(torch.randn(H, W, K, generator=g))
+        c = ident_c[idx] + 0.01 * f + 0.01 * torch.randn(n, 2, generator=g)
+        wh = ident_wh[idx] * (1 + 0.05 * torch.randn(n, 2, generator=g))
+        cand = {"proto": proto, "T2S_feat": torch.zeros(1, 1, 2, 2), "fpn_feat": torch.zeros(1, 1, 2, 2),
+                "box": torch.cat([c - wh / 2, c + wh / 2], 1),
+                "score": 0.2 + 0.75 * torch.rand(n, generator=g),
+                "class": ident_cls[idx].clone(),
+                "mask_coeff": ident_coeff[idx] + 0.1 * torch.randn(n, K, generator=g),
+                "track": torch.nn.functional.normalize(ident_emb[idx] + 0.15 * torch.randn(n, E, generator=g), dim=1),
+                "centerness": torch.rand(n, generator=g)}
+        if n == 0:
+            cand["class"] = torch.zeros(0, dtype=torch.long)
+        for k in ("box", "score", "class", "mask_coeff", "track", "centerness"):
+            out[f"f{f}.det.{k}"] = cand[k].numpy().copy()
+        out[f"f{f}.proto"] = proto.numpy()
+        out[f"f{f}.is_first"] = np.bool_(first)
+        n_shift = len(shifts)
+        det = tracker.track(None, cand, {"is_first": first}, img=None)
+        if len(shifts) > n_shift:
+            out[f"f{f}.shift.loc"], out[f"f{f}.shift.coeff"] = shifts[-1][0].numpy(), shifts[-1][1].numpy()
+            for k, v in shifted[-1].items():
+                out[f"f{f}.shifted.{k}"] = v
+        st = tracker.prev_candidate
+        for k in ("box", "score", "class", "mask_coeff", "track", "centerness", "tracked_mask", "mask"):
+            out[f"f{f}.state.{k}"] = st[k].numpy().copy()
+        out[f"f{f}.out.box_ids"] = np.asarray(det["box_ids"].numpy() if det["box_ids"].numel() else np.zeros(0), np.int64)
+        if det["box_ids"].numel():
+            out[f"f{f}.out.box"] = det["box"].numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "tracker.npz"), **out)
+
+
 def _model_r50():
     """BASELINE.json configs[0] / SURVEY.md 8(c) "Model:" known answer: the reference's own STMask (R50-DCN-FPN
     FCA+TF) on a synthetic 2-frame clip through oracle/ref_model.py; every hot-op call site of frame 2."""
@@ -381,6 +466,7 @@ def main():
     _model_r50()
     _prediction_head()
     _mask_assembly()
+    _tracker()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -23,7 +23,7 @@ DCN_FCB_ADA, DCN_FCB_ALI = 1024, 2048
 DCN_HINT_GATHER = 4096
 CORR_LEAKY_RELU, CORR_RELU, CORR_COPY_FEATS = 1, 2, 4
 DCN_MAX_PROBLEMS = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class StmError(RuntimeError):
@@ -78,6 +78,20 @@ class StmRoiAlignDesc(C.Structure):
     ]
 
 
+class StmTrackState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("n_obj", "box", "score", "cls", "coeff", "track", "centerness", "tracked", "mask_bits", "mask")]
+
+
+class StmTrackDets(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("count", "box", "score", "cls", "coeff", "track", "centerness", "mask_bits", "mask")]
+
+
+class StmTrackParams(C.Structure):
+    _fields_ = [("clips", C.c_int32), ("cap", C.c_int32), ("max_det", C.c_int32), ("k", C.c_int32), ("e", C.c_int32),
+                ("words", C.c_int32), ("hw", C.c_int32), ("max_age", C.c_int32), ("match_coeff", C.c_float * 4),
+                ("bbox_dummy_iou", C.c_float), ("conf_thresh", C.c_float)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "stm_version": (C.c_int, []),
@@ -110,6 +124,8 @@ SIGNATURES = {
                                         C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "stm_mask_iou_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p]),
+    "stm_track_update_fwd": (C.c_int, [C.POINTER(StmTrackParams), C.POINTER(StmTrackState), C.POINTER(StmTrackDets), C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "stm_pool_fc_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "stm_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

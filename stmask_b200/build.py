@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libstmask_b200.so")
-SOURCES = ["abi.cu", "dcn_simt.cu", "dcn_tc.cu", "conv_tma.cu", "corr_simt.cu", "corr_tc.cu", "layout.cu", "roi_align.cu", "temporal_net.cu", "detect_nms.cu", "mask_assembly.cu"]
+SOURCES = ["abi.cu", "dcn_simt.cu", "dcn_tc.cu", "conv_tma.cu", "corr_simt.cu", "corr_tc.cu", "layout.cu", "roi_align.cu", "temporal_net.cu", "detect_nms.cu", "mask_assembly.cu", "track.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
               "-Xptxas", "-v"] + (["-DSTM_DCN_EXPERIMENTS"] if os.environ.get("STM_DCN_EXPERIMENTS") else []) + \

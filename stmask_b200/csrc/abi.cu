@@ -378,6 +378,20 @@ int stm_mask_iou_fwd(const uint32_t* bits_a, const uint32_t* bits_b, const int32
   return launch_mask_iou(bits_a, bits_b, count_a, count_b, iou, frames, max_a, max_b, words, (cudaStream_t)stream);
 }
 
+int stm_track_update_fwd(const StmTrackParams* p, const StmTrackState* st, const StmTrackDets* det, const float* mask_iou,
+                         const uint8_t* is_first, int32_t* det_slot, uint8_t* keep, void* stream) {
+  clear_error();
+  STM_CHECK_ARG(p && st && det, "null descriptor");
+  STM_CHECK_ARG(p->clips >= 0 && p->cap > 0 && p->max_det > 0, "bad clips / cap / max_det");
+  STM_CHECK_ARG(p->k > 0 && p->e > 0 && p->words > 0 && p->hw >= 0, "bad k / e / words / hw");
+  if (p->clips == 0) return STM_OK;
+  STM_CHECK_ARG(st->n_obj && st->box && st->score && st->cls && st->coeff && st->track && st->tracked && st->mask_bits,
+                "tracker state arrays must not be null (mask / centerness may)");
+  STM_CHECK_ARG(det->box && det->score && det->cls && det->coeff && det->track && det->mask_bits, "detection arrays must not be null");
+  STM_CHECK_ARG(mask_iou && det_slot && keep, "mask_iou / det_slot / keep pointer is null");
+  return launch_track_update(*p, *st, *det, mask_iou, is_first, det_slot, keep, (cudaStream_t)stream);
+}
+
 int stm_roi_align_fwd(const StmRoiAlignDesc* d, const void* feat, const float* rois, void* out, void* stream) {
   clear_error();
   STM_CHECK_ARG(d != nullptr, "roi_align descriptor is null");

@@ -146,6 +146,8 @@ int launch_mask_assembly(const float* proto, const float* coeff, const float* bo
                          uint32_t* bits, int frames, int h, int w, int k, int max_n, cudaStream_t stream);
 int launch_mask_iou(const uint32_t* a, const uint32_t* b, const int32_t* na, const int32_t* nb, float* iou, int frames, int max_a,
                     int max_b, int words, cudaStream_t stream);
+int launch_track_update(const StmTrackParams& p, const StmTrackState& st, const StmTrackDets& det, const float* mask_iou,
+                        const uint8_t* is_first, int32_t* det_slot, uint8_t* keep, cudaStream_t stream);
 int launch_roi_align(const StmRoiAlignDesc& d, const void* feat, const float* rois, void* out, cudaStream_t stream);
 
 }  // namespace stm

@@ -405,16 +405,17 @@ TileCfg choose_tile(int batch, int out_h, int out_w, int ex, int ey) {
     const int th = (128 - tw) / bw + 1 < out_h ? (128 - tw) / bw + 1 : out_h;
     const int bh = th + ey;
     int bb = 1;
-    if (th == out_h && tw == out_w) {
-      bb = (128 - ((th - 1) * bw + tw)) / (bh * bw) + 1;
-      if (bb > batch) bb = batch;
-      if (bb < 1) bb = 1;
-    }
+    if (th == out_h && tw == out_w) bb = (128 - ((th - 1) * bw + tw)) / (bh * bw) + 1;       // whole maps: several images per tile
     if (bw > 128 || bh > 128 || bb > 128) continue;
-    const int64_t tiles = (int64_t)((out_w + tw - 1) / tw) * ((out_h + th - 1) / th) * ((batch + bb - 1) / bb);
-    const double eff = (double)batch * out_h * out_w / ((double)tiles * 128.0);
+    // live rows per tile as if the batch were a multiple of bb: which kernel runs (this one or the gather loop, whose
+    // accumulation order differs) must not depend on how a caller chunks its frames
+    const double eff = (double)bb * out_h * out_w / ((double)((out_w + tw - 1) / tw) * ((out_h + th - 1) / th) * 128.0);
     // ties: the smaller box (less halo re-read)
-    if (eff > best.eff + 1e-9 || (eff > best.eff - 1e-9 && bb * bh * bw < best.bb * best.bh * best.bw)) best = TileCfg{tw, th, bb, bw, bh, tiles, eff};
+    if (eff > best.eff + 1e-9 || (eff > best.eff - 1e-9 && bb * bh * bw < best.bb * best.bh * best.bw)) best = TileCfg{tw, th, bb, bw, bh, 0, eff};
+  }
+  if (best.eff > 0.0) {
+    if (best.bb > batch) best.bb = batch > 0 ? batch : 1;
+    best.tiles = (int64_t)((out_w + best.tw - 1) / best.tw) * ((out_h + best.th - 1) / best.th) * ((batch + best.bb - 1) / best.bb);
   }
   return best;
 }
@@ -448,18 +449,19 @@ bool conv_tma_shape_supported(const StmDcnConv* c, const DcnParams& p, const cha
   if (c->in_c % 64 != 0 || c->out_c % 16 != 0 || pick_block_n_tma(c->out_c) == 0) { *why = "channels"; return false; }
   if (c->kernel_h * c->kernel_w > 25 || c->pad_h >= c->kernel_h || c->pad_w >= c->kernel_w) { *why = "kernel / padding"; return false; }
   const int ex = halo_extent(c->kernel_w, c->pad_w, c->stride_w), ey = halo_extent(c->kernel_h, c->pad_h, c->stride_h);
-  int64_t rows = 0, live = 0;
+  double rows = 0, live = 0;
   for (int i = 0; i < p.n_probs; ++i) {
     const DcnProblemDev& q = p.prob[i];
     if (((uintptr_t)q.x & 15) || ((uintptr_t)q.y & 15) || ((q.x_sn | q.x_sh | q.x_sw | q.y_sn | q.y_sh | q.y_sw) & 7)) { *why = "alignment"; return false; }
     if (q.x_sn < 0 || q.x_sh < 0 || q.x_sw < 0) { *why = "negative stride"; return false; }
     const TileCfg t = choose_tile(q.batch, q.out_h, q.out_w, ex, ey);
     if (t.eff <= 0.0) { *why = "no tile"; return false; }
-    rows += t.tiles * 128;
-    live += (int64_t)q.batch * q.out_h * q.out_w;
+    const double px = (double)q.batch * q.out_h * q.out_w;
+    rows += px / t.eff;
+    live += px;
   }
   // dead GEMM rows cost tensor time the gather kernel does not spend: below ~55 % live rows it wins
-  if (rows == 0 || (double)live / (double)rows < 0.55) { *why = "tiles too sparse"; return false; }
+  if (rows <= 0 || live / rows < 0.55) { *why = "tiles too sparse"; return false; }
   return true;
 }
 

@@ -949,3 +949,75 @@ def _correlation_op(x1: torch.Tensor, x2: torch.Tensor, patch_size: int, dilatio
 @_correlation_op.register_fake
 def _(x1, x2, patch_size, dilation_patch, scale, leaky_slope, relu):
     return x1.new_empty((x1.shape[0], patch_size * patch_size, x1.shape[2], x1.shape[3]))
+
+
+def track_update(state: dict, dets: dict, mask_iou: torch.Tensor, is_first: Optional[torch.Tensor], *, match_coeff,
+                 bbox_dummy_iou: float = 0.3, conf_thresh: float = 0.05, max_age: int = 10):
+    """One frame of the tracker's matching state machine for a batch of clips, in place on the device state
+    (Track_TF.track, track_TF.py:52-181; compute_comp_scores, TF_utils.py:98-123).
+
+    state: dict of contiguous device tensors n_obj [C] int32, box [C, cap, 4], score [C, cap], cls [C, cap] int32,
+    coeff [C, cap, k], track [C, cap, e], centerness [C, cap], tracked [C, cap] int32, mask_bits [C, cap, words] int32,
+    mask [C, cap, h, w] (optional).  dets: count [C] int32 (optional), box / score / cls / coeff / track / centerness /
+    mask_bits / mask with max_det rows per clip.  mask_iou [C, max_det, cap] (mask_iou_bits(det bits, state bits)).
+    Returns (det_slot [C, max_det] int32, keep [C, cap] bool); nothing is synchronised."""
+    box = state["box"]
+    _require_cuda(box, "state box")
+    if box.dim() != 3 or box.shape[2] != 4:
+        raise ValueError("state box must be [clips, cap, 4]")
+    clips, cap = box.shape[:2]
+    dbox = dets["box"]
+    if dbox.dim() != 3 or dbox.shape[0] != clips or dbox.shape[2] != 4:
+        raise ValueError("detection box must be [clips, max_det, 4]")
+    max_det = dbox.shape[1]
+    k, e, words = state["coeff"].shape[2], state["track"].shape[2], state["mask_bits"].shape[2]
+    if tuple(mask_iou.shape) != (clips, max_det, cap):
+        raise ValueError(f"mask_iou must be {(clips, max_det, cap)}, got {tuple(mask_iou.shape)}")
+    if len(match_coeff) != 4:
+        raise ValueError("match_coeff needs 4 entries (score, mask IoU, box IoU, label)")
+    want = {"n_obj": ((clips,), torch.int32), "box": ((clips, cap, 4), torch.float32), "score": ((clips, cap), torch.float32),
+            "cls": ((clips, cap), torch.int32), "coeff": ((clips, cap, k), torch.float32), "track": ((clips, cap, e), torch.float32),
+            "tracked": ((clips, cap), torch.int32), "mask_bits": ((clips, cap, words), torch.int32)}
+    for name, (shape, dt) in want.items():
+        t = state[name]
+        if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != box.device:
+            raise ValueError(f"state[{name!r}] must be a contiguous {dt} tensor of shape {shape} on {box.device}")
+    dwant = {"box": ((clips, max_det, 4), torch.float32), "score": ((clips, max_det), torch.float32), "cls": ((clips, max_det), torch.int32),
+             "coeff": ((clips, max_det, k), torch.float32), "track": ((clips, max_det, e), torch.float32),
+             "mask_bits": ((clips, max_det, words), torch.int32)}
+    for name, (shape, dt) in dwant.items():
+        t = dets[name]
+        if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != box.device:
+            raise ValueError(f"dets[{name!r}] must be a contiguous {dt} tensor of shape {shape} on {box.device}")
+    smask, dmask = state.get("mask"), dets.get("mask")
+    hw = 0
+    if smask is not None and dmask is not None:
+        hw = smask[0, 0].numel()
+        if smask.shape[:2] != (clips, cap) or dmask.shape[:2] != (clips, max_det) or dmask[0, 0].numel() != hw or \
+                smask.dtype != torch.float32 or dmask.dtype != torch.float32 or not smask.is_contiguous() or not dmask.is_contiguous():
+            raise ValueError("soft masks must be contiguous float32 [clips, cap, h, w] / [clips, max_det, h, w]")
+    scent, dcent = state.get("centerness"), dets.get("centerness")
+    for t, n, rows in ((scent, "state centerness", cap), (dcent, "dets centerness", max_det)):
+        if t is not None and (tuple(t.shape) != (clips, rows) or t.dtype != torch.float32 or not t.is_contiguous()):
+            raise ValueError(f"{n} must be a contiguous float32 [clips, {rows}] tensor")
+    count = dets.get("count")
+    if count is not None and (count.dtype != torch.int32 or tuple(count.shape) != (clips,)):
+        raise ValueError("dets count must be int32 [clips]")
+    if is_first is not None:
+        is_first = is_first.to(device=box.device, dtype=torch.uint8).contiguous()
+        if tuple(is_first.shape) != (clips,):
+            raise ValueError("is_first must be [clips]")
+    miou = mask_iou.float().contiguous()
+    det_slot = torch.full((clips, max_det), -1, dtype=torch.int32, device=box.device)
+    keep = torch.zeros((clips, cap), dtype=torch.uint8, device=box.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    st = L.StmTrackState(ptr(state["n_obj"]), ptr(box), ptr(state["score"]), ptr(state["cls"]), ptr(state["coeff"]), ptr(state["track"]),
+                         ptr(scent), ptr(state["tracked"]), ptr(state["mask_bits"]), ptr(smask) if hw else None)
+    dt_ = L.StmTrackDets(ptr(count), ptr(dbox), ptr(dets["score"]), ptr(dets["cls"]), ptr(dets["coeff"]), ptr(dets["track"]),
+                         ptr(dcent), ptr(dets["mask_bits"]), ptr(dmask) if hw else None)
+    prm = L.StmTrackParams(clips, cap, max_det, k, e, words, hw, int(max_age), (C.c_float * 4)(*[float(v) for v in match_coeff]),
+                           float(bbox_dummy_iou), float(conf_thresh))
+    with torch.cuda.device(box.device):
+        L.check(L.lib().stm_track_update_fwd(C.byref(prm), C.byref(st), C.byref(dt_), miou.data_ptr(), ptr(is_first), det_slot.data_ptr(),
+                                             keep.data_ptr(), _stream(box)), "stm_track_update_fwd")
+    return det_slot, keep.bool()
