@@ -100,6 +100,9 @@ enum {
    * dtype conv->offset_dtype); every tap's (dy, dx) is derived inside the sampling kernel. */
   STM_DCN_FCB_ADA = 1024,       /* offsets = 1x1 conv_offset(deltas)            (Featurealign.py:20-25,44)   */
   STM_DCN_FCB_ALI = 2048,       /* offsets = closed form of the box transform   (Featurealign.py:46-69)      */
+  STM_DCN_HINT_TAP_MAJOR = 8192, /* K-block order (tap, chunk): sample records computed one tap ahead                        */
+  STM_DCN_HINT_CHUNK_MAJOR = 16384, /* K-block order (chunk, tap) with every tap's sample records resident in shared memory
+                                   (deform_groups == 1; the default for in_c >= 256, N = 256)                 */
   STM_DCN_HINT_GATHER = 4096    /* STM_DCN_ZERO_OFFSET only: keep the plain convolution on the gather main loop instead of
                                    the TMA shifted-view kernel (tests compare the two)                         */
 };

@@ -67,6 +67,8 @@ struct TcArgs {
   int32_t stages;
   int32_t tmem_cols;   // power of two >= M_TILES * block_n
   int32_t pad_;
+  int32_t chunk_outer; // K-block order (chunk, tap) with every tap's sample records resident, instead of (tap, chunk)
+  int32_t pad2_;
 };
 
 template <int M_TILES>
@@ -75,10 +77,11 @@ struct SmemLayout {
   int stage_bytes, meta_p, meta_w, bars, fcb_w, total;
   // pair: each CTA of a cta_group::2 pair holds only its half of the N tile's weight rows;
   // fcb_floats: FCB(ada) conv_offset weights [dg * 2K][4] kept in shared memory
-  __host__ __device__ SmemLayout(int block_n, int stages, bool pair, int fcb_floats = 0) {
+  // meta_bufs: sample-record buffers (3 when the records are computed one tap ahead; all kh*kw taps when resident)
+  __host__ __device__ SmemLayout(int block_n, int stages, bool pair, int fcb_floats = 0, int meta_bufs = META_BUFS) {
     stage_bytes = M_TILES * A_TILE_BYTES + (pair ? block_n / 2 : block_n) * 128;
     int off = stages * stage_bytes;
-    meta_p = off; off += META_BUFS * ROWS * 16;    // per row: top-left corner pointer + 2 flag bits, four bf16 corner weights
+    meta_p = off; off += meta_bufs * ROWS * 16;    // per row: top-left corner pointer + 2 flag bits, four bf16 corner weights
     meta_w = off;
     bars = off;   off += (2 * MAX_STAGES + 2) * 8;
     fcb_w = off;  off += (fcb_floats * 4 + 15) & ~15;
@@ -141,7 +144,8 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   static_assert(D >= 1 && D <= TPK && TPK % D == 0, "gather look-ahead must divide the tasks per K block");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const SmemLayout<M_TILES> L(a.block_n, a.stages, PAIR, FCB ? a.p.dg * 2 * a.p.kh * a.p.kw * 4 : 0);
+  const bool CO = !PLAIN && a.chunk_outer != 0;      // (chunk, tap) K-block order, all taps' records resident (dg == 1)
+  const SmemLayout<M_TILES> L(a.block_n, a.stages, PAIR, FCB ? a.p.dg * 2 * a.p.kh * a.p.kw * 4 : 0, CO ? a.p.kh * a.p.kw : META_BUFS);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* accum_bar = empty_bar + MAX_STAGES;
@@ -267,8 +271,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       }
     };
     // DCN border rule: the sample is 0 outside (-1, H) x (-1, W); corners outside the map add 0.
-    auto compute_meta = [&](int it_, float oy, float ox, float mk, float r3) {
-      const int buf = it_ % META_BUFS;
+    auto compute_meta = [&](int buf, int it_, float oy, float ox, float mk, float r3) {
       const int tap_ = it_ / p.dg, g_ = it_ - tap_ * p.dg;
       const int ti = tap_ / p.kw, tj = tap_ - ti * p.kw;
       if (FCB) {
@@ -393,9 +396,27 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     GTask S[D];                             // task (kb, j) lives in S[j % D]; D tasks are in flight per thread
     float r_oy, r_ox, r_mk, r_3;
     // prologue: metadata of iteration 0, then the first D gather tasks of K block 0
-    load_raw(0, r_oy, r_ox, r_mk, r_3);
-    compute_meta(0, r_oy, r_ox, r_mk, r_3);
-    load_raw(1, r_oy, r_ox, r_mk, r_3);
+    if (CO) {
+      // every tap's record up front (dg == 1: iteration == tap).  The raw loads of three taps are in flight together
+      // (FCB: the four box deltas are the same for every tap and are loaded once).
+      if (FCB) {
+        load_raw(0, r_oy, r_ox, r_mk, r_3);
+        for (int t = 0; t < K; ++t) compute_meta(t, t, r_oy, r_ox, r_mk, r_3);
+      } else {
+        for (int t0 = 0; t0 < K; t0 += 3) {
+          float a_oy[3], a_ox[3], a_mk[3], a_3[3];
+#pragma unroll
+          for (int u = 0; u < 3; ++u) load_raw(t0 + u < K ? t0 + u : n_iter, a_oy[u], a_ox[u], a_mk[u], a_3[u]);
+#pragma unroll
+          for (int u = 0; u < 3; ++u)
+            if (t0 + u < K) compute_meta(t0 + u, t0 + u, a_oy[u], a_ox[u], a_mk[u], a_3[u]);
+        }
+      }
+    } else {
+      load_raw(0, r_oy, r_ox, r_mk, r_3);
+      compute_meta(0, 0, r_oy, r_ox, r_mk, r_3);
+      load_raw(1, r_oy, r_ox, r_mk, r_3);
+    }
     named_barrier_sync(1, PT);
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -408,17 +429,20 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     int it = 0, cc = 0;                     // (tap, group) iteration and channel chunk of the CURRENT K block
 #pragma unroll 1
     for (int kb = 0; kb < num_kb; ++kb) {
-      if (cc == 0 && it + 1 < n_iter) {
+      if (!CO && cc == 0 && it + 1 < n_iter) {
         // metadata one iteration ahead: buffer (it+1) % 3 was last read by the gather of iteration it-2, which
         // every thread finished before it arrived at the previous barrier
-        compute_meta(it + 1, r_oy, r_ox, r_mk, r_3);
+        compute_meta((it + 1) % META_BUFS, it + 1, r_oy, r_ox, r_mk, r_3);
         load_raw(it + 2, r_oy, r_ox, r_mk, r_3);
         named_barrier_sync(1, PT);
       }
-      int nit = it, ncc = cc + 1;
-      if (ncc == chunks) { ncc = 0; nit = it + 1; }
+      // next K block: tap-major (tap, chunk) or, with resident records, chunk-major (chunk, tap) — consecutive K blocks
+      // then read the SAME 128 bytes of neighbouring pixels, which is what lets L1 serve the taps' overlap
+      int nit, ncc;
+      if (CO) { nit = it + 1; ncc = cc; if (nit == K) { nit = 0; ncc = cc + 1; } }
+      else { nit = it; ncc = cc + 1; if (ncc == chunks) { ncc = 0; nit = it + 1; } }
       const bool has_next = kb + 1 < num_kb;
-      const int cbuf = it % META_BUFS, nbuf = nit % META_BUFS;
+      const int cbuf = CO ? it : it % META_BUFS, nbuf = CO ? nit : nit % META_BUFS;
       const uint32_t ccoff = (uint32_t)((cc * BLOCK_K + v * 8) * 2), ncoff = (uint32_t)((ncc * BLOCK_K + v * 8) * 2);
       mbar_wait(&empty_bar[stage], phase ^ 1u);
       const uint32_t a_dst = smem_u32(smem + stage * L.stage_bytes) + dst_off;
@@ -505,12 +529,14 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       uint32_t phase = 0;
       // a pair splits the N tile: this CTA loads weight rows [n0 + rank * block_n/2, + block_n/2)
       const int nrow0 = PAIR ? n0 + (int)cta_rank * (block_n / 2) : n0;
+      const int outer = CO ? chunks : K, inner = CO ? K : chunks;       // CO: dg == 1
 #pragma unroll 1
-      for (int tap = 0; tap < K; ++tap)
+      for (int o = 0; o < outer; ++o)
 #pragma unroll 1
         for (int g = 0; g < p.dg; ++g)
 #pragma unroll 1
-          for (int cc = 0; cc < chunks; ++cc) {
+          for (int i = 0; i < inner; ++i) {
+            const int tap = CO ? i : o, cc = CO ? o : i;
             mbar_wait_relaxed(&empty_bar[s], phase ^ 1u);
             uint8_t* dst = smem + s * L.stage_bytes + M_TILES * A_TILE_BYTES;
             const int kcol = tap * p.in_c + g * cpd + cc * BLOCK_K;
@@ -617,8 +643,8 @@ int launch_t(const TcArgs& args, const CUtensorMap& tmap, dim3 grid, int smem_by
 // call's arguments and the device's SM count (no environment variables, no mutable state), shared by the
 // launcher and by stm_deform_conv2d_variant().
 struct TcPlan {
-  int block_n, n_tiles, m_tiles, pw, stages, smem_bytes, tmem_cols, blocks, grid_x;
-  bool two_ctas, pair, plain, fcb;
+  int block_n, n_tiles, m_tiles, pw, stages, smem_bytes, tmem_cols, blocks, grid_x, meta_bufs;
+  bool two_ctas, pair, plain, fcb, chunk_outer;
 };
 
 int make_plan(const StmDcnConv* conv, const DcnParams& p, TcPlan* out) {
@@ -678,8 +704,20 @@ int make_plan(const StmDcnConv* conv, const DcnParams& p, TcPlan* out) {
   int budget = pl.m_tiles == 2 ? 172 * 1024 : (pl.two_ctas ? (pl.pair ? 82 * 1024 : 110 * 1024) : 132 * 1024);
   budget += (fcb_floats * 4 + 15) & ~15;
   if ((conv->flags & STM_DCN_HINT_DEEP_PIPE) != 0) budget = 200 * 1024;
+  // chunk-major K order: all kh*kw sample records of a row stay in shared memory (16 B each), so consecutive K blocks are
+  // the neighbouring taps of ONE 64-channel chunk and re-read each other's cache lines from L1 instead of L2
+  // (B200, FCB 3x5 over 1024 frames, power-capped: 14.36 -> 14.10 ms; equal at full clocks — the kernel is bound by L1
+  // wavefronts, hits and misses alike, and what the order saves is L2 traffic, i.e. power).  Only with >= 4 chunks per tap
+  // and N = 256: at C = 128 the records' 12 KB come out of an L1 that two 3-stage CTAs have already cut to ~40 KB
+  // (0.304 -> 0.394 ms on the 48x80 layer).  STM_DCN_HINT_CHUNK_MAJOR / _TAP_MAJOR force either order.
+  pl.chunk_outer = !pl.plain && p.dg == 1 && p.in_c > BLOCK_K && p.kh * p.kw > 1 && p.kh * p.kw <= 25 &&
+                   (conv->flags & STM_DCN_HINT_TAP_MAJOR) == 0 &&
+                   ((p.in_c >= 4 * BLOCK_K && pl.block_n == 256) || (conv->flags & STM_DCN_HINT_CHUNK_MAJOR) != 0);
+  pl.meta_bufs = pl.chunk_outer ? p.kh * p.kw : META_BUFS;
+  if (pl.chunk_outer) budget += (pl.meta_bufs - META_BUFS) * rows_per_cta * 16;
   auto total = [&](int st) {
-    return pl.m_tiles == 2 ? SmemLayout<2>(pl.block_n, st, pl.pair, fcb_floats).total : SmemLayout<1>(pl.block_n, st, pl.pair, fcb_floats).total;
+    return pl.m_tiles == 2 ? SmemLayout<2>(pl.block_n, st, pl.pair, fcb_floats, pl.meta_bufs).total
+                           : SmemLayout<1>(pl.block_n, st, pl.pair, fcb_floats, pl.meta_bufs).total;
   };
   pl.stages = MAX_STAGES;
   for (; pl.stages > 2; --pl.stages)
@@ -727,8 +765,9 @@ int dcn_tc_variant(const StmDcnConv* conv, const DcnParams& p, char* buf, size_t
   TcPlan pl;
   const int rc = make_plan(conv, p, &pl);
   if (rc != STM_OK) return rc;
-  snprintf(buf, len, "tcgen05 rows=%d n=%d pair=%d plain=%d fcb=%d producer_warps=%d stages=%d ctas_per_sm=%d grid=%dx%d", TILE_M * pl.m_tiles,
-           pl.block_n, pl.pair ? 1 : 0, pl.plain ? 1 : 0, pl.fcb ? 1 : 0, pl.pw, pl.stages, pl.two_ctas ? 2 : 1, pl.grid_x, pl.n_tiles);
+  snprintf(buf, len, "tcgen05 rows=%d n=%d pair=%d plain=%d fcb=%d producer_warps=%d stages=%d ctas_per_sm=%d korder=%s grid=%dx%d", TILE_M * pl.m_tiles,
+           pl.block_n, pl.pair ? 1 : 0, pl.plain ? 1 : 0, pl.fcb ? 1 : 0, pl.pw, pl.stages, pl.two_ctas ? 2 : 1, pl.chunk_outer ? "chunk" : "tap",
+           pl.grid_x, pl.n_tiles);
   return STM_OK;
 }
 
@@ -761,6 +800,8 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   args.tmem_cols = pl.tmem_cols;
   args.pad_ = (conv->flags >> 20) & 0xff;      // experiment bits (profiling only; undocumented, results identical)
   args.stages = pl.stages;
+  args.chunk_outer = pl.chunk_outer ? 1 : 0;
+  args.pad2_ = 0;
 
   CUtensorMap tmap;
   const cuuint64_t ktot = (cuuint64_t)p.kh * p.kw * p.in_c;

@@ -240,3 +240,48 @@ def test_feature_align_module_uses_the_fused_path(cuda_device):
                                                m.conv_adaption.spec(), relu=True)
         for a, b in zip(fused, two_step):
             assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) <= 1e-2     # same samples up to fp32 rounding of the offsets: bf16 ulps
+
+
+# ------------------------------------------------------------------------------------------
+# K-block order: chunk-major with resident sample records (default, dg == 1) vs tap-major (STM_DCN_HINT_TAP_MAJOR)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [("fcb", (3, 5), 256, 256, 1), ("fcb", (5, 3), 256, 256, 1), ("dcnv2", (3, 3), 128, 128, 1),
+                                  ("dcnv2", (3, 3), 256, 256, 2), ("dcnv2", (3, 3), 512, 512, 2)],
+                         ids=lambda c: f"{c[0]}_{c[1][0]}x{c[1][1]}_C{c[2]}_s{c[4]}")
+def test_k_order_variants_vs_oracle(cuda_device, case):
+    """Both K orders of the tcgen05 sampling kernel against the oracle, and the plan reports which one runs."""
+    ops, L = _ops()
+    kind, (kh, kw), cin, cout, s = case
+    pad = ((kh - 1) // 2, (kw - 1) // 2)
+    rng = np.random.default_rng(kh * 5 + kw + cin + s)
+    B, H, W = 6, 26, 44
+    spec = ops.ConvSpec(cin, cout, (kh, kw), s, pad)
+    Ho, Wo = spec.out_hw(H, W)
+    w = q(rng.standard_normal((cout, cin, kh, kw)) / np.sqrt(cin * kh * kw))
+    x = q(rng.standard_normal((B, cin, H, W)))
+    wp = ops.pack_weight(dev(w, BF16, cuda_device, cl=False), spec, BF16)
+    xd = dev(x, BF16, cuda_device)
+    v_auto = ops.deform_conv2d_variant([tuple(xd.shape)], spec, BF16, fcb=kind == "fcb")
+    v_chunk = ops.deform_conv2d_variant([tuple(xd.shape)], spec, BF16, hint=L.DCN_HINT_CHUNK_MAJOR, fcb=kind == "fcb")
+    v_tap = ops.deform_conv2d_variant([tuple(xd.shape)], spec, BF16, hint=L.DCN_HINT_TAP_MAJOR, fcb=kind == "fcb")
+    assert "korder=chunk" in v_chunk and "korder=tap" in v_tap, (v_chunk, v_tap)
+    assert ("korder=chunk" in v_auto) == (cin >= 256), v_auto          # C = 128 keeps its L1 for the gather
+    if kind == "fcb":
+        deltas = rng.standard_normal((B, 4, Ho, Wo)).astype(np.float32)
+        w_off = (rng.standard_normal((2 * kh * kw, 4, 1, 1)) * 0.5).astype(np.float32)
+        want = oracle.feature_align(x, deltas, w, (kh, kw), w_offset=w_off)[0]
+        dd, wod = dev(deltas, torch.float32, cuda_device), dev(w_off, torch.float32, cuda_device, cl=False)
+        run = lambda hint: ops.deform_conv2d_fcb_multi([xd], [dd], wp, spec, wod, relu=True, hint=hint)[0]
+    else:
+        off = (rng.standard_normal((B, 2 * kh * kw, Ho, Wo)) * 2).astype(np.float32)
+        msk = rng.standard_normal((B, kh * kw, Ho, Wo)).astype(np.float32)
+        bias = rng.standard_normal(cout).astype(np.float32)
+        want = oracle.deform_conv2d(x, off, w, bias, 1.0 / (1.0 + np.exp(-msk)), stride=s, padding=pad)
+        od, md, bd = dev(off, torch.float32, cuda_device), dev(msk, torch.float32, cuda_device), dev(bias, torch.float32, cuda_device, cl=False)
+        run = lambda hint: ops.deform_conv2d_multi([xd], [od], [md], wp, bd, spec, mask_sigmoid=True, hint=hint)[0]
+    CM = L.DCN_HINT_CHUNK_MAJOR
+    for hint in (0, CM, L.DCN_HINT_TAP_MAJOR, L.DCN_HINT_ROWS256 | CM, L.DCN_HINT_ROWS128 | L.DCN_HINT_NO_PAIR | CM, L.DCN_HINT_TWO_CTAS | CM):
+        y = run(hint)
+        torch.cuda.synchronize()
+        err = rel_err(y.float().cpu().numpy(), want)
+        assert err <= TOL, (case, hint, err)

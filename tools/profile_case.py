@@ -1,5 +1,5 @@
 """Run ONE hot-path operator a few times (for ncu captures and quick timing).
-    python tools/profile_case.py fcb35|fcb33|fcb53|bb128s2|bb128|bb256|bb512s2|corr|corrpairs|corrsweep|roialign [--frames 72] [--reps 5] [--backend auto]
+    python tools/profile_case.py fcb35|fcb33|fcb53|fused35|bb128s2|bb128|bb256|bb512s2|headconv|corr|corrpairs|corrsweep|roialign [--frames 72] [--reps 5] [--backend auto]
 """
 import argparse
 import os
@@ -99,6 +99,17 @@ elif a.case.startswith("bb"):
     pc([x], cw, cb, s, 1, 1, out_f32=True)
     a.case += ".predictor"
     timeit(lambda: pc([x], cw, cb, s, 1, 1, out_f32=True), flops=2.0 * F * Ho * Wo * C * 32 * 9)
+elif a.case == "headconv":      # a 256 -> 256 3x3 conv + ReLU of the prediction head over P3..P7: ONE launch of the TMA shifted-view kernel
+    lv = fpn_level_sizes()
+    spec = ops.ConvSpec(256, 256, 3, 1, 1)
+    w = (torch.randn(256, 256, 3, 3, device=dev) / (256 * 9) ** 0.5).bfloat16()
+    wp = ops.pack_weight(w, spec, torch.bfloat16)
+    bias = torch.randn(256, device=dev)
+    xs = [torch.randn(F, 256, h, ww, device=dev).bfloat16().contiguous(memory_format=torch.channels_last) for h, ww in lv]
+    outs = ops.deform_conv2d_multi(xs, [None] * 5, None, wp, bias, spec, relu=True, hint=a.hint)
+    print(ops.deform_conv2d_variant([tuple(x.shape) for x in xs], spec, torch.bfloat16, a.backend, a.hint, zero_offset=True))
+    timeit(lambda: ops.deform_conv2d_multi(xs, [None] * 5, None, wp, bias, spec, relu=True, outs=outs, hint=a.hint),
+           flops=2.0 * F * sum(h * ww for h, ww in lv) * 256 * 256 * 9)
 elif a.case == "corr":
     n = F - 1
     x1 = torch.randn(n, 256, 24, 40, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
