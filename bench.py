@@ -642,9 +642,15 @@ def layer_table(hp, inp, n_local, peaks, reps, backend):
             tp = _time_launches(lambda: m._predictor([x], com.weight, com.bias, com.stride, com.padding, com.dilation, out_f32=True), reps)
         fl = float(n_local) * s.flops_per_frame
         n_same = sum(1 for q in hp.dcn_shapes if (q.channels, q.in_h, q.in_w, q.stride) == key)
+        # the offset / mask-logit predictor (a regular 3x3 conv to 27 -> 32 fp32 channels) is judged on HBM bytes: it reads x once
+        # and writes its fp32 output once
+        pbytes = float(x.numel() * x.element_size() + om.numel() * om.element_size())
         rows.append({"layer": f"backbone DCNv2 C={s.channels} {s.in_h}x{s.in_w} s{s.stride} (x{n_same})", "ms": t, "tflops": fl / t / 1e9,
-                     "frac": fl / t / 1e9 / peaks["bf16_burst"], "predictor_ms": tp,
-                     "variant": ops.deform_conv2d_variant([tuple(x.shape)], spec, x.dtype, backend)})
+                     "frac": fl / t / 1e9 / peaks["bf16_burst"], "predictor_ms": tp, "predictor_gbs": pbytes / tp / 1e6,
+                     "predictor_frac_hbm": pbytes / tp / 1e6 / peaks["hbm_gbs"],
+                     "variant": ops.deform_conv2d_variant([tuple(x.shape)], spec, x.dtype, backend),
+                     "predictor_variant": ops.deform_conv2d_variant([tuple(x.shape)], ops.ConvSpec(s.channels, 32, 3, s.stride, 1), x.dtype, backend,
+                                                                    zero_offset=True)})
     px = sum(h * w for h, w in hp.level_sizes)
     for k, m in enumerate(hp.fcb):
         kh, kw = m.kernel_size

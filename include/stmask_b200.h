@@ -103,6 +103,7 @@ enum {
   STM_DCN_HINT_TAP_MAJOR = 8192, /* K-block order (tap, chunk): sample records computed one tap ahead                        */
   STM_DCN_HINT_CHUNK_MAJOR = 16384, /* K-block order (chunk, tap) with every tap's sample records resident in shared memory
                                    (deform_groups == 1; the default for in_c >= 256, N = 256)                 */
+  STM_DCN_HINT_NO_FUSE = 32768, /* STM_DCN_ZERO_OFFSET only: TMA kernel without the horizontal taps fused into N (tests)      */
   STM_DCN_HINT_GATHER = 4096    /* STM_DCN_ZERO_OFFSET only: keep the plain convolution on the gather main loop instead of
                                    the TMA shifted-view kernel (tests compare the two)                         */
 };

@@ -21,7 +21,7 @@ DCN_HINT_ROWS128, DCN_HINT_ROWS256, DCN_HINT_NO_PAIR = 16, 32, 64
 DCN_OUT_F32, DCN_HINT_DEEP_PIPE, DCN_HINT_TWO_CTAS = 128, 256, 512
 DCN_FCB_ADA, DCN_FCB_ALI = 1024, 2048
 DCN_HINT_GATHER = 4096
-DCN_HINT_TAP_MAJOR, DCN_HINT_CHUNK_MAJOR = 8192, 16384
+DCN_HINT_TAP_MAJOR, DCN_HINT_CHUNK_MAJOR, DCN_HINT_NO_FUSE = 8192, 16384, 32768
 CORR_LEAKY_RELU, CORR_RELU, CORR_COPY_FEATS = 1, 2, 4
 DCN_MAX_PROBLEMS = 8
 ABI_VERSION = 6

@@ -33,7 +33,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int MAX_SA = 4;
+constexpr int MAX_SA = 6;
 constexpr int MAX_SB = 40;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int NUM_THREADS = 192;
@@ -56,7 +56,9 @@ struct ConvTmaArgs {
   int32_t chunks, kh, kw, ph, pw;
   int32_t sa, sb, a_stage_bytes, a_phase_bytes, resident;
   int32_t tmem_cols, flags;
-  int32_t exp_, pad_;                  // experiment bits (profiling only)
+  int32_t exp_;                        // experiment bits (profiling only)
+  int32_t fuse_kw;                     // > 0: the kw horizontal taps are fused into the GEMM's N (see FUSE below)
+  int32_t n_mma, pad_;                 // UMMA N = block_n, or block_n * kw when fused
   const float* bias;
 };
 
@@ -98,12 +100,19 @@ __device__ __forceinline__ void tap_axis(int j, int pad, int& parity, int& shift
   shift = ((t - parity) >> 1) - lat0;
 }
 
-template <int S, int TAPS>
+// FUSE (stride 1, small Cout — the offset / mask predictors): with N = 32 the tensor core spends its time re-reading the A
+// tile from shared memory once per tap (profiles/r02_tma_predictor_bb256.txt: operand reads 60 % of the shared-memory pipe,
+// tensor pipe 25 %).  The kw horizontal taps are therefore moved from K into N: one MMA per (vertical tap, K slice) with
+// B = [Cout x kw] weight rows (a 4-D TMA box of the OHWI weight: row n * kw + j) computes P_j[m] = sum_c x[m] w[n, i, j, c]
+// for every input pixel m of the tile, and out[m] = P_0[m] + P_1[m + 1] + P_2[m + 2] is formed in the epilogue with two
+// warp shuffles per channel (rows m + 1, m + 2 of the next lane quarter come through shared memory).  A third of the MMAs,
+// a third of the A reads.
+template <int S, int TAPS, bool FUSE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ ConvTmaMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int b_slot_bytes = a.block_n * 128;
+  const int b_slot_bytes = a.n_mma * 128;
   uint8_t* sA = smem;
   uint8_t* sB = smem + a.sa * a.a_stage_bytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + a.sb * b_slot_bytes);
@@ -115,10 +124,11 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);       // [block_n]
   uint32_t* s_tapoff = reinterpret_cast<uint32_t*>(s_bias + a.block_n);   // [problem][tap]: descriptor offset of the tap's view
+  float* s_xchg = reinterpret_cast<float*>(s_tapoff + STM_DCN_MAX_PROBLEMS * MAX_TAPS);   // FUSE: [2][4 quarters][3][block_n]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int taps = a.kh * a.kw;
+  const int taps = FUSE ? a.kh : a.kh * a.kw;                   // A views (and weight slices) per 64-channel chunk
   const int items = a.chunks * taps;                            // weight slices per tile
   const bool resident = a.resident != 0;
 
@@ -136,7 +146,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
       const int pi = i / MAX_TAPS, tap = i - pi * MAX_TAPS;
       uint32_t off = 0;
       if (tap < taps) {
-        const int ti = tap / a.kw, tj = tap - ti * a.kw;
+        const int ti = FUSE ? tap : tap / a.kw, tj = FUSE ? 0 : tap - ti * a.kw;
         int pyi, sy, pxi, sx;
         tap_axis<S>(ti, a.ph, pyi, sy);
         tap_axis<S>(tj, a.pw, pxi, sx);
@@ -190,13 +200,15 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
               if (first) {
                 const int slot = c * taps + tap;
                 mbar_arrive_expect_tx(&b_full[slot], (uint32_t)b_slot_bytes);
-                tma_load_2d(sB + slot * b_slot_bytes, &maps.w, &b_full[slot], kcol, n0);
+                if (FUSE) tma_load_4d(sB + slot * b_slot_bytes, &maps.w, &b_full[slot], c * 64, 0, tap, n0);
+                else tma_load_2d(sB + slot * b_slot_bytes, &maps.w, &b_full[slot], kcol, n0);
               }
             } else {
               const uint32_t slot = bslot;
               mbar_wait_relaxed(&b_empty[slot], bphase ^ 1u);
               mbar_arrive_expect_tx(&b_full[slot], (uint32_t)b_slot_bytes);
-              tma_load_2d(sB + slot * b_slot_bytes, &maps.w, &b_full[slot], kcol, n0);
+              if (FUSE) tma_load_4d(sB + slot * b_slot_bytes, &maps.w, &b_full[slot], c * 64, 0, tap, n0);
+              else tma_load_2d(sB + slot * b_slot_bytes, &maps.w, &b_full[slot], kcol, n0);
               if (++bslot == (uint32_t)a.sb) { bslot = 0; bphase ^= 1u; }
             }
           }
@@ -211,13 +223,12 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
     // per dependent instruction): the per-tap work is therefore a table lookup (descriptor offset of the tap's shifted
     // view, 16-byte units), two 64-bit adds and the four MMAs, fully unrolled for 3x3.
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)a.block_n);
+      const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)a.n_mma);
       const uint32_t bstep = (uint32_t)(b_slot_bytes >> 4);
       const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB));
       uint32_t ac = 0, tl = 0, bslot = 0, bphase = 0, astage = 0, aphase = 0;
       constexpr int NT = TAPS > 0 ? TAPS : 1;
-      uint32_t toff[NT];
-      int cur_pi = -1;
+      uint32_t toff[NT] = {};
 #ifdef STM_CONV_TMA_TRACE
       long long t_acc = 0, t_a = 0, t_b = 0, t_all = clock64(), tq;
 #define TRACE_T0 tq = clock64()
@@ -230,8 +241,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++tl) {
         const TileAt t = decode_tile(a, tile);
         const uint32_t* tab = s_tapoff + t.pi * MAX_TAPS;
-        if (TAPS > 0 && t.pi != cur_pi) {
-          cur_pi = t.pi;
+        if (TAPS > 0) {                                                // (a handful of LDS per tile)
 #pragma unroll
           for (int i = 0; i < NT; ++i) toff[i] = tab[i];
         }
@@ -240,8 +250,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
         mbar_wait_relaxed(&acc_empty[buf], ((tl >> 1) & 1u) ^ 1u);     // the epilogue has drained this accumulator
         TRACE_ADD(t_acc);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * (uint32_t)a.block_n;
-        const bool b_ready = resident && tl > 0;                       // every weight slice is already in shared memory
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)a.n_mma;
+        const bool b_ready = resident && tl > 0 && !(a.exp_ & 8);                       // every weight slice is already in shared memory
 #pragma unroll 1
         for (int c = 0; c < a.chunks; ++c) {
           const uint32_t s = astage;
@@ -341,7 +351,67 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
       const uint32_t buf = tl & 1u;
       if (a.exp_ & 4) mbar_wait_relaxed(&acc_full[buf], (tl >> 1) & 1u); else mbar_wait(&acc_full[buf], (tl >> 1) & 1u);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * (uint32_t)a.block_n;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * (uint32_t)a.n_mma;
+      if (FUSE) {
+        // column n * 3 + j holds P_j of output channel n for THIS row's pixel; out[m] = P_0[m] + P_1[m + 1] + P_2[m + 2]
+        float* xq = s_xchg + ((tl & 1u) * 4 + q4) * 3 * a.block_n;            // what this quarter's rows 0 and 1 give the one below
+        const float* xn = s_xchg + ((tl & 1u) * 4 + ((q4 + 1) & 3)) * 3 * a.block_n;
+#pragma unroll 1
+        for (int c0 = 0; c0 < a.block_n; c0 += 16) {
+          uint32_t v[48];
+          {
+            uint32_t t0[16], t1[16], t2[16];
+            tmem_ld16(taddr + (uint32_t)(c0 * 3), t0);
+            tmem_ld16(taddr + (uint32_t)(c0 * 3 + 16), t1);
+            tmem_ld16(taddr + (uint32_t)(c0 * 3 + 32), t2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { v[i] = t0[i]; v[16 + i] = t1[i]; v[32 + i] = t2[i]; }
+          }
+          if (lane < 2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (lane == 0) { xq[c0 + i] = __uint_as_float(v[3 * i + 1]); xq[a.block_n + c0 + i] = __uint_as_float(v[3 * i + 2]); }
+              else xq[2 * a.block_n + c0 + i] = __uint_as_float(v[3 * i + 2]);
+            }
+          }
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p1 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[3 * i + 1]), 1);
+            const float p2 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[3 * i + 2]), 2);
+            f[i] = __uint_as_float(v[3 * i]);
+            if (lane < 31) f[i] += p1;
+            if (lane < 30) f[i] += p2;
+          }
+          // rows m + 1 / m + 2 of the last two lanes live in the next quarter: wait for its boundary values
+          // (both buffers of s_xchg alternate with the tile, so one barrier per 16 channels orders publish -> consume)
+          named_barrier_sync(2, EPI_THREADS);
+          if (lane >= 30 && q4 < 3) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (lane == 31) f[i] += xn[c0 + i] + xn[2 * a.block_n + c0 + i];
+              else f[i] += xn[a.block_n + c0 + i];
+            }
+          }
+          if (ok && !(a.exp_ & 2)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              f[i] += s_bias[c0 + i];
+              if (relu) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (out_f32) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(q.y) + yoff + c0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(q.y) + yoff + c0);
+              dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+              dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < a.block_n; c0 += 16) {
         uint32_t acc[16];
@@ -364,6 +434,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
             dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
           }
         }
+      }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -397,15 +468,17 @@ int halo_extent(int k, int pad, int stride) {
 
 // TH x TW output pixels (x BB images when a whole map is smaller than a tile) with (TH - 1) * BW + TW <= 128 GEMM rows:
 // the choice that leaves the fewest dead rows over the whole feature map
-TileCfg choose_tile(int batch, int out_h, int out_w, int ex, int ey) {
+TileCfg choose_tile(int batch, int out_h, int out_w, int ex, int ey, int reserve = 0) {
+  const int M = 128 - reserve;          // GEMM rows a tile's outputs may span (fused horizontal taps read `reserve` rows further)
   TileCfg best{};
   best.eff = -1.0;
   for (int tw = 1; tw <= out_w && tw <= 128; ++tw) {
     const int bw = tw + ex;
-    const int th = (128 - tw) / bw + 1 < out_h ? (128 - tw) / bw + 1 : out_h;
+    if (tw > M) break;
+    const int th = (M - tw) / bw + 1 < out_h ? (M - tw) / bw + 1 : out_h;
     const int bh = th + ey;
     int bb = 1;
-    if (th == out_h && tw == out_w) bb = (128 - ((th - 1) * bw + tw)) / (bh * bw) + 1;       // whole maps: several images per tile
+    if (th == out_h && tw == out_w) bb = (M - ((th - 1) * bw + tw)) / (bh * bw) + 1;       // whole maps: several images per tile
     if (bw > 128 || bh > 128 || bb > 128) continue;
     // live rows per tile as if the batch were a multiple of bb: which kernel runs (this one or the gather loop, whose
     // accumulation order differs) must not depend on how a caller chunks its frames
@@ -434,7 +507,12 @@ int pick_block_n_tma(int out_c) {
   return 0;
 }
 
-SmemAttrCache g_conv_tma_attr[4];
+SmemAttrCache g_conv_tma_attr[6];
+
+// horizontal taps fused into N: stride 1, 3x3, one N tile whose kw-fold still fits one UMMA (N <= 256) — the predictors
+bool fuse_kw_ok(const StmDcnConv* c) {
+  return c->stride_h == 1 && c->kernel_h == 3 && c->kernel_w == 3 && c->out_c * 3 <= 96 && (c->flags & STM_DCN_HINT_NO_FUSE) == 0;
+}
 
 }  // namespace
 
@@ -454,7 +532,7 @@ bool conv_tma_shape_supported(const StmDcnConv* c, const DcnParams& p, const cha
     const DcnProblemDev& q = p.prob[i];
     if (((uintptr_t)q.x & 15) || ((uintptr_t)q.y & 15) || ((q.x_sn | q.x_sh | q.x_sw | q.y_sn | q.y_sh | q.y_sw) & 7)) { *why = "alignment"; return false; }
     if (q.x_sn < 0 || q.x_sh < 0 || q.x_sw < 0) { *why = "negative stride"; return false; }
-    const TileCfg t = choose_tile(q.batch, q.out_h, q.out_w, ex, ey);
+    const TileCfg t = choose_tile(q.batch, q.out_h, q.out_w, ex, ey, fuse_kw_ok(c) ? c->kernel_w - 1 : 0);
     if (t.eff <= 0.0) { *why = "no tile"; return false; }
     const double px = (double)q.batch * q.out_h * q.out_w;
     rows += px / t.eff;
@@ -479,11 +557,13 @@ static int make_conv_tma_plan(const StmDcnConv* conv, const DcnParams& p, ConvTm
   a.exp_ = (conv->flags >> 20) & 0xff;
   a.bias = p.bias;
   const int ex = halo_extent(p.kw, p.pw, S), ey = halo_extent(p.kh, p.ph, S);
+  a.fuse_kw = fuse_kw_ok(conv) ? p.kw : 0;
+  a.n_mma = a.fuse_kw ? a.block_n * a.fuse_kw : a.block_n;
   int64_t sp_tiles = 0, live = 0;
   int phase_rows = 0;
   for (int i = 0; i < p.n_probs; ++i) {
     const DcnProblemDev& q = p.prob[i];
-    const TileCfg t = choose_tile(q.batch, q.out_h, q.out_w, ex, ey);
+    const TileCfg t = choose_tile(q.batch, q.out_h, q.out_w, ex, ey, a.fuse_kw ? a.fuse_kw - 1 : 0);
     ConvTmaProb& d = a.prob[i];
     d.y = q.y; d.y_sn = q.y_sn; d.y_sh = q.y_sh; d.y_sw = q.y_sw;
     d.batch = q.batch; d.out_h = q.out_h; d.out_w = q.out_w;
@@ -503,9 +583,11 @@ static int make_conv_tma_plan(const StmDcnConv* conv, const DcnParams& p, ConvTm
   pl.eff = sp_tiles ? (double)live / ((double)sp_tiles * 128.0) : 0.0;
   a.a_phase_bytes = (phase_rows * 128 + 1023) & ~1023;
   a.a_stage_bytes = a.a_phase_bytes * (S == 2 ? 4 : 1);
-  const int b_slot = a.block_n * 128;
-  const int fixed = (2 * MAX_SA + 2 * MAX_SB + 4) * 8 + 16 + a.block_n * 4 + STM_DCN_MAX_PROBLEMS * MAX_TAPS * 4 + 1024;
-  const int items = a.chunks * p.kh * p.kw;
+  const int b_slot = a.n_mma * 128;
+  const int fixed = (2 * MAX_SA + 2 * MAX_SB + 4) * 8 + 16 + a.block_n * 4 + STM_DCN_MAX_PROBLEMS * MAX_TAPS * 4 +
+                    (a.fuse_kw ? 2 * 4 * 3 * a.block_n * 4 : 0) + 1024;
+  const int views = a.fuse_kw ? p.kh : p.kh * p.kw;          // A views = weight slices per chunk
+  const int items = a.chunks * views;
   a.sa = 2;
   int room = SMEM_LIMIT - fixed - a.sa * a.a_stage_bytes;
   int sb = room / b_slot;
@@ -516,15 +598,16 @@ static int make_conv_tma_plan(const StmDcnConv* conv, const DcnParams& p, ConvTm
     sb = items;
   } else {
     // a ring: one chunk's worth of taps in flight is plenty; spend what is left on a third / fourth input stage
-    const int want = p.kh * p.kw + 3 < 12 ? 12 : p.kh * p.kw + 3;
+    const int want = views + 3 < 12 ? 12 : views + 3;
     if (sb > want) sb = want;
   }
   a.sb = sb;
   room = SMEM_LIMIT - fixed - a.sa * a.a_stage_bytes - sb * b_slot;
-  while (a.sa < MAX_SA && a.sa < 3 && room >= a.a_stage_bytes) { ++a.sa; room -= a.a_stage_bytes; }
+  // a stage lives for only kh (fused) .. kh*kw tap views: the TMA round trip is hidden by the number of stages in flight
+  while (a.sa < MAX_SA && room >= a.a_stage_bytes) { ++a.sa; room -= a.a_stage_bytes; }
   pl.smem_bytes = fixed + a.sa * a.a_stage_bytes + sb * b_slot;
   int cols = 32;
-  while (cols < 2 * a.block_n) cols <<= 1;
+  while (cols < 2 * a.n_mma) cols <<= 1;
   a.tmem_cols = cols;
   const int sms = device_sm_count();
   pl.grid = a.total_tiles < sms ? a.total_tiles : sms;
@@ -537,8 +620,8 @@ int conv_tma_variant(const StmDcnConv* conv, const DcnParams& p, char* buf, size
   const int rc = make_conv_tma_plan(conv, p, &pl);
   if (rc != STM_OK) return rc;
   const ConvTmaArgs& a = pl.args;
-  snprintf(buf, len, "tcgen05 tma-conv stride=%d n=%d tile=%dx%dx%d live=%.2f plain=1 a_stages=%d w_slots=%d resident=%d grid=%d tiles=%d", pl.stride,
-           a.block_n, a.prob[0].bb, a.prob[0].th, a.prob[0].tw, pl.eff, a.sa, a.sb, a.resident, pl.grid, a.total_tiles);
+  snprintf(buf, len, "tcgen05 tma-conv stride=%d n=%d fused_taps=%d tile=%dx%dx%d live=%.2f plain=1 a_stages=%d w_slots=%d resident=%d grid=%d tiles=%d",
+           pl.stride, a.block_n, a.fuse_kw, a.prob[0].bb, a.prob[0].th, a.prob[0].tw, pl.eff, a.sa, a.sb, a.resident, pl.grid, a.total_tiles);
   return STM_OK;
 }
 
@@ -564,7 +647,17 @@ int launch_conv_tma(const StmDcnConv* conv, const DcnParams& p, cudaStream_t str
     if (r != CUDA_SUCCESS) { set_error("tma conv: cuTensorMapEncodeTiled(x) failed (%d)", (int)r); return STM_ERR_CUDA; }
   }
   for (int i = p.n_probs; i < STM_DCN_MAX_PROBLEMS; ++i) maps.x[i] = maps.x[0];
-  {
+  if (pl.args.fuse_kw) {
+    // OHWI weight [n][i][j][c] as a 4-D tensor (c, j, i, n): the box {64, kw, 1, N} of vertical tap i lands as rows n * kw + j
+    const cuuint64_t dims[4] = {(cuuint64_t)p.in_c, (cuuint64_t)p.kw, (cuuint64_t)p.kh, (cuuint64_t)p.out_c};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.in_c * 2, (cuuint64_t)p.kw * p.in_c * 2, (cuuint64_t)p.kh * p.kw * p.in_c * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)p.kw, 1, (cuuint32_t)pl.args.block_n};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.w), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tma conv: cuTensorMapEncodeTiled(w, fused) failed (%d)", (int)r); return STM_ERR_CUDA; }
+  } else {
     const cuuint64_t ktot = (cuuint64_t)p.kh * p.kw * p.in_c;
     const cuuint64_t dims[2] = {ktot, (cuuint64_t)p.out_c};
     const cuuint64_t strides[1] = {ktot * 2};
@@ -575,15 +668,16 @@ int launch_conv_tma(const StmDcnConv* conv, const DcnParams& p, cudaStream_t str
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tma conv: cuTensorMapEncodeTiled(w) failed (%d)", (int)r); return STM_ERR_CUDA; }
   }
-#define STM_CONV_GO(S_, T_, SLOT_)                                                                                 \
+#define STM_CONV_GO(S_, T_, F_, SLOT_)                                                                             \
   do {                                                                                                             \
-    const int rc2 = ensure_dynamic_smem(conv_tma_kernel<S_, T_>, pl.smem_bytes, g_conv_tma_attr[SLOT_]);          \
+    const int rc2 = ensure_dynamic_smem(conv_tma_kernel<S_, T_, F_>, pl.smem_bytes, g_conv_tma_attr[SLOT_]);      \
     if (rc2 != STM_OK) return rc2;                                                                                 \
-    conv_tma_kernel<S_, T_><<<pl.grid, NUM_THREADS, pl.smem_bytes, stream>>>(pl.args, maps);                      \
+    conv_tma_kernel<S_, T_, F_><<<pl.grid, NUM_THREADS, pl.smem_bytes, stream>>>(pl.args, maps);                  \
   } while (0)
   const bool k33 = p.kh == 3 && p.kw == 3;
-  if (S == 1) { if (k33) STM_CONV_GO(1, 9, 0); else STM_CONV_GO(1, 0, 1); }
-  else { if (k33) STM_CONV_GO(2, 9, 2); else STM_CONV_GO(2, 0, 3); }
+  if (pl.args.fuse_kw) { if (pl.args.exp_ & 16) STM_CONV_GO(1, 0, true, 5); else STM_CONV_GO(1, 3, true, 4); }
+  else if (S == 1) { if (k33) STM_CONV_GO(1, 9, false, 0); else STM_CONV_GO(1, 0, false, 1); }
+  else { if (k33) STM_CONV_GO(2, 9, false, 2); else STM_CONV_GO(2, 0, false, 3); }
 #undef STM_CONV_GO
   count_launch();
   STM_CUDA_OK(cudaGetLastError());

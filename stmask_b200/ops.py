@@ -295,7 +295,7 @@ def deform_conv2d_multi(xs: Sequence[torch.Tensor], offsets: Sequence[Optional[t
         p.y = y.data_ptr()
         p.y_stride_n, p.y_stride_h, p.y_stride_w = y.stride(0), y.stride(2), y.stride(3)
     flags = (L.DCN_RELU if relu else 0) | (L.DCN_MASK_SIGMOID if mask_sigmoid else 0) | (L.DCN_ZERO_OFFSET if zero_offset else 0)
-    flags |= int(hint) & (L.DCN_HINT_ROWS128 | L.DCN_HINT_ROWS256 | L.DCN_HINT_NO_PAIR | L.DCN_HINT_DEEP_PIPE | L.DCN_HINT_TWO_CTAS | L.DCN_HINT_GATHER | L.DCN_HINT_TAP_MAJOR | L.DCN_HINT_CHUNK_MAJOR | (0xff << 20))
+    flags |= int(hint) & (L.DCN_HINT_ROWS128 | L.DCN_HINT_ROWS256 | L.DCN_HINT_NO_PAIR | L.DCN_HINT_DEEP_PIPE | L.DCN_HINT_TWO_CTAS | L.DCN_HINT_GATHER | L.DCN_HINT_TAP_MAJOR | L.DCN_HINT_CHUNK_MAJOR | L.DCN_HINT_NO_FUSE | (0xff << 20))
     if out_f32:
         flags |= L.DCN_OUT_F32
     conv = spec.c_struct(xdt, odt, flags, _BACKENDS[backend])

@@ -31,6 +31,8 @@ CASES = [
     (64, 16, (1, 1), 1, (0, 0), [(2, 17, 29)], False, False),           # 1x1
     (192, 48, (1, 1), 1, (0, 0), [(21, 3, 5)], True, True),             # several images per tile
     (128, 32, (3, 3), 2, (1, 1), [(3, 25, 39)], True, False),           # stride 2 on odd sizes
+    (256, 32, (3, 3), 1, (1, 1), [(3, 48, 80), (3, 11, 17), (5, 3, 5)], True, True),    # fused horizontal taps: ragged maps, several images per tile
+    (64, 16, (3, 3), 1, (1, 1), [(2, 9, 130)], False, False),          # fused taps, a map wider than a tile
 ]
 
 
@@ -53,7 +55,13 @@ def test_tma_conv_vs_cudnn_fp32_and_gather_path(cuda_device, case):
     ys = ops.deform_conv2d_multi(xs, [None] * len(xs), [None] * len(xs), wp, b, spec, relu=relu, out_f32=out_f32)
     yg = ops.deform_conv2d_multi(xs, [None] * len(xs), [None] * len(xs), wp, b, spec, relu=relu, out_f32=out_f32,
                                  hint=L.DCN_HINT_GATHER)
+    fused = s == 1 and k == (3, 3) and cout <= 32
+    assert ("fused_taps=3" in v) == fused, v
+    yn = ops.deform_conv2d_multi(xs, [None] * len(xs), [None] * len(xs), wp, b, spec, relu=relu, out_f32=out_f32, hint=L.DCN_HINT_NO_FUSE)
+    assert "fused_taps=0" in ops.deform_conv2d_variant([tuple(x.shape) for x in xs], spec, torch.bfloat16, zero_offset=True, hint=L.DCN_HINT_NO_FUSE)
     torch.cuda.synchronize()
+    for y, y3 in zip(ys, yn):
+        assert rel_err(y.float().cpu().numpy(), y3.float().cpu().numpy()) <= (1e-4 if out_f32 else 1e-2)
     for x, y, y2 in zip(xs, ys, yg):
         want = _ref(x, w, b, s, pad, relu)
         assert y.shape == want.shape and y.dtype == (torch.float32 if out_f32 else torch.bfloat16)
