@@ -633,13 +633,13 @@ def layer_table(hp, inp, n_local, peaks, reps, backend):
         x = inp[f"dcn{i}.x"]
         com = m.conv_offset_mask
         with torch.no_grad():
-            om = m._predictor([x], com.weight, com.bias, com.stride, com.padding, com.dilation, out_f32=True)[0]
+            om = m._predictor([x], com.weight, com.bias, com.stride, com.padding, com.dilation, out_f32=True, out_planar=True)[0]
             spec = m._spec()
             wp, bf = m._cache.weight(m.weight, spec, x.dtype), m._cache.bias(m.bias)
             y = ops.deform_conv2d_multi([x], [om[:, :18]], [om[:, 18:27]], wp, bf, spec, mask_sigmoid=True, backend=backend)
             t = _time_launches(lambda: ops.deform_conv2d_multi([x], [om[:, :18]], [om[:, 18:27]], wp, bf, spec, mask_sigmoid=True,
                                                                backend=backend, outs=y), reps)
-            tp = _time_launches(lambda: m._predictor([x], com.weight, com.bias, com.stride, com.padding, com.dilation, out_f32=True), reps)
+            tp = _time_launches(lambda: m._predictor([x], com.weight, com.bias, com.stride, com.padding, com.dilation, out_f32=True, out_planar=True), reps)
         fl = float(n_local) * s.flops_per_frame
         n_same = sum(1 for q in hp.dcn_shapes if (q.channels, q.in_h, q.in_w, q.stride) == key)
         # the offset / mask-logit predictor (a regular 3x3 conv to 27 -> 32 fp32 channels) is judged on HBM bytes: it reads x once

@@ -104,6 +104,10 @@ enum {
   STM_DCN_HINT_CHUNK_MAJOR = 16384, /* K-block order (chunk, tap) with every tap's sample records resident in shared memory
                                    (deform_groups == 1; the default for in_c >= 256, N = 256)                 */
   STM_DCN_HINT_NO_FUSE = 32768, /* STM_DCN_ZERO_OFFSET only: TMA kernel without the horizontal taps fused into N (tests)      */
+  STM_DCN_OUT_PLANAR = 131072,  /* y is [batch, out_c, out_h, out_w] ("NCHW"): element (b, n, h, w) at b * y_stride_n + n * (out_h * y_stride_h)
+                                   + h * y_stride_h + w * y_stride_w.  tcgen05 backend only.  A DCN's offset / mask predictor writes
+                                   this layout so that the sampling kernel's per-tap offset loads of 32 neighbouring pixels are one
+                                   128-byte line instead of 32 (they were 39 % of its L1 requests on the C = 128 stage)            */
   STM_DCN_HINT_GATHER = 4096    /* STM_DCN_ZERO_OFFSET only: keep the plain convolution on the gather main loop instead of
                                    the TMA shifted-view kernel (tests compare the two)                         */
 };

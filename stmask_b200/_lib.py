@@ -19,6 +19,7 @@ BACKEND_NAMES = {BACKEND_AUTO: "auto", BACKEND_SIMT: "simt", BACKEND_TCGEN05: "t
 DCN_RELU, DCN_MASK_SIGMOID, DCN_ZERO_OFFSET = 1, 2, 4
 DCN_HINT_ROWS128, DCN_HINT_ROWS256, DCN_HINT_NO_PAIR = 16, 32, 64
 DCN_OUT_F32, DCN_HINT_DEEP_PIPE, DCN_HINT_TWO_CTAS = 128, 256, 512
+DCN_OUT_PLANAR = 131072
 DCN_FCB_ADA, DCN_FCB_ALI = 1024, 2048
 DCN_HINT_GATHER = 4096
 DCN_HINT_TAP_MAJOR, DCN_HINT_CHUNK_MAJOR, DCN_HINT_NO_FUSE = 8192, 16384, 32768

@@ -76,12 +76,14 @@ class DCN(DCNv2):
         # predictor is this library's own regular convolution (zero-offset mode of the same tcgen05 main loop)
         # with the bias fused and the fp32 accumulators stored as fp32: sampling positions are never rounded to
         # bf16.  cat(o1, o2) is the first 2/3 of its channels, so the sampling kernel reads offsets and mask logits
-        # straight out of that [B, Ho, Wo, 32] tensor (views, no copies) and applies the sigmoid while sampling.
+        # straight out of that tensor (views, no copies) and applies the sigmoid while sampling.  On the tcgen05 path the
+        # predictor writes it plane-major ([B, 32, Ho, Wo] contiguous): the sampling kernel's per-tap loads of 32
+        # neighbouring pixels' offsets are then one 128-byte line instead of 32.
         ops._no_grad_inputs(input, self.weight, self.bias, self.conv_offset_mask.weight, self.conv_offset_mask.bias)
         n_off = 2 * self.deformable_groups * self.kernel_size[0] * self.kernel_size[1]
         n_all = n_off + n_off // 2
         com = self.conv_offset_mask
-        om = self._predictor([input], com.weight, com.bias, com.stride, com.padding, com.dilation, out_f32=True)[0]
+        om = self._predictor([input], com.weight, com.bias, com.stride, com.padding, com.dilation, out_f32=True, out_planar=True)[0]
         spec = self._spec()
         return ops.deform_conv2d_multi([input], [om[:, :n_off]], [om[:, n_off:n_all]],
                                        self._cache.weight(self.weight, spec, input.dtype),

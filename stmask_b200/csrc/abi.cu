@@ -87,7 +87,8 @@ static int validate_problems(const StmDcnConv* c, const StmDcnProblem* pr, int n
     STM_CHECK_ARG((int64_t)q.batch * oh * ow < (1ll << 31), "problem %d: too many output pixels", i);
     if (q.batch == 0) continue;
     STM_CHECK_ARG(q.x != nullptr && q.y != nullptr, "problem %d: x/y pointer is null", i);
-    STM_CHECK_ARG(q.x_stride_w >= c->in_c && q.y_stride_w >= c->out_c, "problem %d: NHWC pixel stride smaller than C", i);
+    STM_CHECK_ARG(q.x_stride_w >= c->in_c && ((c->flags & STM_DCN_OUT_PLANAR) ? q.y_stride_w >= 1 : q.y_stride_w >= c->out_c),
+                  "problem %d: NHWC pixel stride smaller than C", i);
     STM_CHECK_ARG((int64_t)q.in_h * q.x_stride_h < (1ll << 31) && q.x_stride_h >= 0 && q.x_stride_w >= 0,
                   "problem %d: one image of x must span < 2^31 elements", i);
     if (!(c->flags & STM_DCN_ZERO_OFFSET)) STM_CHECK_ARG(q.offset != nullptr, "problem %d: offset pointer is null", i);
@@ -244,6 +245,7 @@ int stm_deform_conv2d_fwd(const StmDcnConv* c, const StmDcnProblem* pr, int32_t 
   fill_params(c, pr, n, w_packed, bias, &p);
   if (p.n_probs == 0) return STM_OK;
   if (be == STM_BACKEND_TCGEN05) return launch_dcn_tc(c, p, workspace, ws_bytes, (cudaStream_t)stream);
+  if (c->flags & STM_DCN_OUT_PLANAR) { set_error("STM_DCN_OUT_PLANAR needs the tcgen05 backend"); return STM_ERR_UNSUPPORTED; }
   return launch_dcn_simt(p, c->dtype, c->offset_dtype, (cudaStream_t)stream);
 }
 

@@ -42,7 +42,7 @@ constexpr int MAX_TAPS = 25;
 
 struct ConvTmaProb {
   void* y;
-  int64_t y_sn, y_sh, y_sw;
+  int64_t y_sn, y_sh, y_sw, y_sc;      // y_sc: channel stride (1 = NHWC; out_h * y_sh for STM_DCN_OUT_PLANAR)
   int32_t batch, out_h, out_w;
   int32_t tw, th, bb, bw, bh;          // tile: output columns / rows / images; TMA box columns / rows (per parity tile)
   int32_t tiles_x, tiles_y, tiles_b;
@@ -347,7 +347,8 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
       const int r = rem / q.bw, cc = rem - r * q.bw;
       const int b = t.b0 + bi, ho = t.h0 + r, wo = t.w0 + cc;
       const bool ok = bi < q.bb && r < q.th && cc < q.tw && b < q.batch && ho < q.out_h && wo < q.out_w;
-      const int64_t yoff = ok ? (b * q.y_sn + ho * q.y_sh + wo * q.y_sw + n0) : 0;
+      const int64_t yoff = ok ? (b * q.y_sn + ho * q.y_sh + wo * q.y_sw + n0 * q.y_sc) : 0;
+      const bool planar = q.y_sc != 1;
       const uint32_t buf = tl & 1u;
       if (a.exp_ & 4) mbar_wait_relaxed(&acc_full[buf], (tl >> 1) & 1u); else mbar_wait(&acc_full[buf], (tl >> 1) & 1u);
       tcgen05_fence_after();
@@ -400,7 +401,14 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
               f[i] += s_bias[c0 + i];
               if (relu) f[i] = fmaxf(f[i], 0.f);
             }
-            if (out_f32) {
+            if (planar) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int64_t o = yoff + (int64_t)(c0 + i) * q.y_sc;
+                if (out_f32) reinterpret_cast<float*>(q.y)[o] = f[i];
+                else reinterpret_cast<__nv_bfloat16*>(q.y)[o] = __float2bfloat16_rn(f[i]);
+              }
+            } else if (out_f32) {
               float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(q.y) + yoff + c0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
@@ -424,7 +432,14 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
             f[i] = __uint_as_float(acc[i]) + s_bias[c0 + i];
             if (relu) f[i] = fmaxf(f[i], 0.f);
           }
-          if (out_f32) {
+          if (planar) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int64_t o = yoff + (int64_t)(c0 + i) * q.y_sc;
+                if (out_f32) reinterpret_cast<float*>(q.y)[o] = f[i];
+                else reinterpret_cast<__nv_bfloat16*>(q.y)[o] = __float2bfloat16_rn(f[i]);
+              }
+            } else if (out_f32) {
             float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(q.y) + yoff + c0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
@@ -530,7 +545,9 @@ bool conv_tma_shape_supported(const StmDcnConv* c, const DcnParams& p, const cha
   double rows = 0, live = 0;
   for (int i = 0; i < p.n_probs; ++i) {
     const DcnProblemDev& q = p.prob[i];
-    if (((uintptr_t)q.x & 15) || ((uintptr_t)q.y & 15) || ((q.x_sn | q.x_sh | q.x_sw | q.y_sn | q.y_sh | q.y_sw) & 7)) { *why = "alignment"; return false; }
+    const bool planar = (c->flags & STM_DCN_OUT_PLANAR) != 0;
+    if (((uintptr_t)q.x & 15) || ((q.x_sn | q.x_sh | q.x_sw) & 7)) { *why = "alignment"; return false; }
+    if (!planar && (((uintptr_t)q.y & 15) || ((q.y_sn | q.y_sh | q.y_sw) & 7))) { *why = "alignment"; return false; }
     if (q.x_sn < 0 || q.x_sh < 0 || q.x_sw < 0) { *why = "negative stride"; return false; }
     const TileCfg t = choose_tile(q.batch, q.out_h, q.out_w, ex, ey, fuse_kw_ok(c) ? c->kernel_w - 1 : 0);
     if (t.eff <= 0.0) { *why = "no tile"; return false; }
@@ -566,6 +583,7 @@ static int make_conv_tma_plan(const StmDcnConv* conv, const DcnParams& p, ConvTm
     const TileCfg t = choose_tile(q.batch, q.out_h, q.out_w, ex, ey, a.fuse_kw ? a.fuse_kw - 1 : 0);
     ConvTmaProb& d = a.prob[i];
     d.y = q.y; d.y_sn = q.y_sn; d.y_sh = q.y_sh; d.y_sw = q.y_sw;
+    d.y_sc = (p.flags & STM_DCN_OUT_PLANAR) ? (int64_t)q.out_h * q.y_sh : 1;
     d.batch = q.batch; d.out_h = q.out_h; d.out_w = q.out_w;
     d.tw = t.tw; d.th = t.th; d.bb = t.bb; d.bw = t.bw; d.bh = t.bh;
     d.tiles_x = (q.out_w + t.tw - 1) / t.tw;

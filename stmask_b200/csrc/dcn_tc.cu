@@ -498,6 +498,8 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     }
     const bool relu = (p.flags & STM_DCN_RELU) != 0;
     const bool out_f32 = (p.flags & STM_DCN_OUT_F32) != 0;
+    const bool planar = (p.flags & STM_DCN_OUT_PLANAR) != 0;       // y[b][n][ho][wo]: consecutive lanes = consecutive pixels
+    const int64_t y_sc = (int64_t)pr.out_h * pr.y_sh;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * block_n);
     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
       uint32_t acc[16];
@@ -511,7 +513,14 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
           if (p.bias != nullptr) f[i] += __ldg(p.bias + n0 + c0 + i);
           if (relu) f[i] = fmaxf(f[i], 0.f);
         }
-        if (out_f32) {
+        if (planar) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int64_t o = yoff + (int64_t)(n0 + c0 + i) * y_sc;
+            if (out_f32) reinterpret_cast<float*>(pr.y)[o] = f[i];
+            else reinterpret_cast<__nv_bfloat16*>(pr.y)[o] = __float2bfloat16_rn(f[i]);
+          }
+        } else if (out_f32) {
           float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(pr.y) + yoff + n0 + c0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
@@ -748,8 +757,9 @@ bool dcn_tc_shape_supported(const StmDcnConv* c, const StmDcnProblem* pr, int n,
   for (int i = 0; i < n; ++i) {
     const StmDcnProblem& q = pr[i];
     if (q.batch == 0) continue;
-    if (((uintptr_t)q.x & 15) || ((uintptr_t)q.y & 15)) { *why = "x / y not 16-byte aligned"; return false; }
-    if ((q.x_stride_n | q.x_stride_h | q.x_stride_w | q.y_stride_n | q.y_stride_h | q.y_stride_w) & 7) {
+    if (((uintptr_t)q.x & 15) || (!(c->flags & STM_DCN_OUT_PLANAR) && ((uintptr_t)q.y & 15))) { *why = "x / y not 16-byte aligned"; return false; }
+    const bool planar = (c->flags & STM_DCN_OUT_PLANAR) != 0;      // scalar stores: no alignment demand on y
+    if (((q.x_stride_n | q.x_stride_h | q.x_stride_w) & 7) || (!planar && ((q.y_stride_n | q.y_stride_h | q.y_stride_w) & 7))) {
       *why = "x / y strides not multiples of 8 elements";
       return false;
     }
@@ -777,7 +787,7 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   TcArgs args;
   args.p = p_in;
   DcnParams& p = args.p;
-  p.flags &= 0xffff;
+  p.flags &= 0x2ffff;                          // public flags (bit 16 is internal)
   if (pl_fcb_needs_weight(p) && p.fcb_w == nullptr) { set_error("FCB(ada) needs the conv_offset weight"); return STM_ERR_INVALID_ARGUMENT; }
   if (conv->offset_dtype == STM_BF16) p.flags |= FLAG_OFFSETS_BF16;
   {

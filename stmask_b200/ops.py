@@ -206,13 +206,16 @@ def deform_conv2d_multi(xs: Sequence[torch.Tensor], offsets: Sequence[Optional[t
                         bias_f32: Optional[torch.Tensor], spec: ConvSpec, *, relu: bool = False,
                         mask_sigmoid: bool = False, backend: str = "auto",
                         outs: Optional[Sequence[torch.Tensor]] = None, hint: int = 0,
-                        out_f32: bool = False) -> List[torch.Tensor]:
+                        out_f32: bool = False, out_planar: bool = False) -> List[torch.Tensor]:
     """One launch over several feature maps that share one weight (e.g. the FPN levels of the
     shared prediction head, reference STMask.py:91-92 / prediction_head_FC.py:166-167).
 
     offsets[i] is None for every i  =>  plain convolution through the same kernel.
     out_f32: the outputs are float32 whatever the activations' dtype (the fp32 accumulators are stored as they
     are) — what the offset / mask-logit predictor of a DCN wants: sampling positions must not be rounded to bf16.
+    out_planar: the outputs are contiguous [B, Cout, Ho, Wo] ("NCHW") tensors instead of channels-last ones (tcgen05
+    backend only; silently channels-last when the call runs on the CUDA-core kernel) — the layout in which a sampling
+    kernel's per-tap offset loads of neighbouring pixels coalesce.
     """
     n = len(xs)
     if n == 0:
@@ -275,8 +278,10 @@ def deform_conv2d_multi(xs: Sequence[torch.Tensor], offsets: Sequence[Optional[t
         if outs is not None:
             y = outs[i]
             if tuple(y.shape) != (b, spec.out_c, ho, wo) or y.dtype != (torch.float32 if out_f32 else x.dtype) or \
-                    not (spec.out_c == 1 or y.stride(1) == 1):
-                raise ValueError("preallocated output must be a channels-last tensor of the right shape/dtype")
+                    not (spec.out_c == 1 or (y.stride(1) == ho * y.stride(2) if out_planar else y.stride(1) == 1)):
+                raise ValueError("preallocated output must be a channels-last (or, with out_planar, plane-major) tensor of the right shape/dtype")
+        elif out_planar:
+            y = torch.empty((b, spec.out_c, ho, wo), dtype=torch.float32 if out_f32 else x.dtype, device=dev)
         else:
             y = torch.empty((b, spec.out_c, ho, wo), dtype=torch.float32 if out_f32 else x.dtype, device=dev,
                             memory_format=torch.channels_last)
@@ -298,7 +303,21 @@ def deform_conv2d_multi(xs: Sequence[torch.Tensor], offsets: Sequence[Optional[t
     flags |= int(hint) & (L.DCN_HINT_ROWS128 | L.DCN_HINT_ROWS256 | L.DCN_HINT_NO_PAIR | L.DCN_HINT_DEEP_PIPE | L.DCN_HINT_TWO_CTAS | L.DCN_HINT_GATHER | L.DCN_HINT_TAP_MAJOR | L.DCN_HINT_CHUNK_MAJOR | L.DCN_HINT_NO_FUSE | (0xff << 20))
     if out_f32:
         flags |= L.DCN_OUT_F32
+    if out_planar:
+        flags |= L.DCN_OUT_PLANAR
     conv = spec.c_struct(xdt, odt, flags, _BACKENDS[backend])
+    if out_planar and L.lib().stm_deform_conv2d_backend(C.byref(conv), probs, n) != L.BACKEND_TCGEN05:
+        # the CUDA-core kernel writes channels-last only: same values, the other memory format
+        if outs is not None:
+            raise ValueError("out_planar outputs were preallocated but this call runs on the CUDA-core kernel")
+        flags &= ~L.DCN_OUT_PLANAR
+        conv = spec.c_struct(xdt, odt, flags, _BACKENDS[backend])
+        for i in range(n):
+            y = torch.empty(tuple(ys[i].shape), dtype=ys[i].dtype, device=dev, memory_format=torch.channels_last)
+            ys[i] = y
+            keep.append(y)
+            probs[i].y = y.data_ptr()
+            probs[i].y_stride_n, probs[i].y_stride_h, probs[i].y_stride_w = y.stride(0), y.stride(2), y.stride(3)
     if bias_f32 is not None:
         _require_cuda(bias_f32, "bias")
         if bias_f32.dtype != torch.float32 or tuple(bias_f32.shape) != (spec.out_c,) or not bias_f32.is_contiguous():
@@ -480,13 +499,15 @@ class PlainConv:
 
     def __call__(self, xs: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor], stride: IntPair = 1,
                  padding: IntPair = 0, dilation: IntPair = 1, *, relu: bool = False, out_f32: bool = False,
-                 in_pad: Optional[Tuple[int, int]] = None, backend: str = "auto", hint: int = 0) -> List[torch.Tensor]:
-        """-> list of [B, Cout_padded, Ho, Wo] channels-last tensors (slice [:, :Cout] is the convolution)."""
+                 in_pad: Optional[Tuple[int, int]] = None, backend: str = "auto", hint: int = 0,
+                 out_planar: bool = False) -> List[torch.Tensor]:
+        """-> list of [B, Cout_padded, Ho, Wo] channels-last tensors (slice [:, :Cout] is the convolution); with
+        `out_planar` contiguous plane-major ("NCHW") tensors when the call runs on the tcgen05 kernels."""
         _no_grad_inputs(weight, bias, *xs)
         wp, b, cp = self._refresh(weight, bias, xs[0].dtype, in_pad)
         spec = ConvSpec(xs[0].shape[1], cp, weight.shape[2:], stride, padding, dilation)
         return deform_conv2d_multi(list(xs), [None] * len(xs), None, wp, b, spec, relu=relu, backend=backend, hint=hint,
-                                   out_f32=out_f32)
+                                   out_f32=out_f32, out_planar=out_planar)
 
 
 def fcb_ali_offsets(shape: torch.Tensor, kernel_size: IntPair, dtype: Optional[torch.dtype] = None) -> torch.Tensor:

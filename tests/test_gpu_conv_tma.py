@@ -86,3 +86,28 @@ def test_tma_conv_writes_only_its_own_pixels(cuda_device):
     assert float((big[..., cout:] - 7.0).abs().max()) == 0.0
     want = _ref(x, w, None, 1, 1, False)
     assert rel_err(out.float().cpu().numpy(), want.cpu().numpy()) <= 1e-2
+
+
+@pytest.mark.parametrize("case", [(256, 32, 1, [(5, 24, 40)]), (128, 32, 2, [(3, 48, 80)]), (256, 64, 1, [(2, 12, 20), (2, 6, 10)]),
+                                  (640, 512, 1, [(3, 7, 7)])], ids=lambda c: f"C{c[0]}_N{c[1]}_s{c[2]}")
+def test_plane_major_output_equals_channels_last(cuda_device, case):
+    """STM_DCN_OUT_PLANAR: the same convolution written as contiguous [B, C, H, W] planes (fused-tap TMA kernel, plain TMA
+    kernel, stride 2, and the gather main loop on 7x7 crops); fp32 and bf16 outputs."""
+    from stmask_b200 import ops
+    cin, cout, s, maps = case
+    g = torch.Generator(device=cuda_device).manual_seed(cin + cout + s)
+    w = (torch.randn((cout, cin, 3, 3), generator=g, device=cuda_device) / (cin * 9) ** 0.5).bfloat16()
+    b = torch.randn((cout,), generator=g, device=cuda_device)
+    xs = [torch.randn((B, cin, H, W), generator=g, device=cuda_device).bfloat16().contiguous(memory_format=torch.channels_last) for B, H, W in maps]
+    spec = ops.ConvSpec(cin, cout, 3, s, 1)
+    wp = ops.pack_weight(w, spec, torch.bfloat16)
+    for f32 in (True, False):
+        a = ops.deform_conv2d_multi(xs, [None] * len(xs), None, wp, b, spec, relu=True, out_f32=f32)
+        p = ops.deform_conv2d_multi(xs, [None] * len(xs), None, wp, b, spec, relu=True, out_f32=f32, out_planar=True)
+        torch.cuda.synchronize()
+        for ya, yp in zip(a, p):
+            assert yp.is_contiguous() and ya.is_contiguous(memory_format=torch.channels_last)
+            assert torch.equal(ya, yp)
+    # fp32 activations run on the CUDA-core kernel: channels-last result, same API
+    y32 = ops.deform_conv2d_multi([xs[0].float()], [None], None, ops.pack_weight(w.float(), spec, torch.float32), b, spec, out_planar=True)[0]
+    assert y32.is_contiguous(memory_format=torch.channels_last)

@@ -20,6 +20,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--backend", default="auto")
 ap.add_argument("--offset-scale", type=float, default=2.0)
 ap.add_argument("--hint", type=int, default=0, help="STM_DCN_HINT_* bits (16 rows128, 32 rows256, 64 no-pair, 256 deep pipe)")
+ap.add_argument("--nhwc-offsets", action="store_true", help="bb*: offsets / mask logits as a channels-last [B, Ho, Wo, 32] tensor (round-2 first half)")
 a = ap.parse_args()
 dev = "cuda"
 torch.manual_seed(0)
@@ -86,7 +87,9 @@ elif a.case.startswith("bb"):
     w = (torch.randn(C, C, 3, 3, device=dev) / (C * 9) ** 0.5).bfloat16()
     wp = ops.pack_weight(w, spec, torch.bfloat16)
     x = torch.randn(F, C, H, W, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
-    om = (torch.randn(F, 32, Ho, Wo, device=dev) * (a.offset_scale / 2.0)).contiguous(memory_format=torch.channels_last)   # fp32, as the predictor writes it
+    om = torch.randn(F, 32, Ho, Wo, device=dev) * (a.offset_scale / 2.0)   # fp32, plane-major, as the predictor writes it
+    if a.nhwc_offsets:
+        om = om.contiguous(memory_format=torch.channels_last)
     bias = torch.randn(C, device=dev)
     outs = ops.deform_conv2d_multi([x], [om[:, :18]], [om[:, 18:27]], wp, bias, spec, mask_sigmoid=True, backend=a.backend, hint=a.hint)
     print(ops.deform_conv2d_variant([tuple(x.shape)], spec, torch.bfloat16, a.backend, a.hint))
@@ -96,9 +99,9 @@ elif a.case.startswith("bb"):
     pc = ops.PlainConv()
     cw = (torch.randn(27, C, 3, 3, device=dev) * 0.02).bfloat16()
     cb = torch.randn(27, device=dev).bfloat16()
-    pc([x], cw, cb, s, 1, 1, out_f32=True)
+    pc([x], cw, cb, s, 1, 1, out_f32=True, out_planar=True)
     a.case += ".predictor"
-    timeit(lambda: pc([x], cw, cb, s, 1, 1, out_f32=True), flops=2.0 * F * Ho * Wo * C * 32 * 9)
+    timeit(lambda: pc([x], cw, cb, s, 1, 1, out_f32=True, out_planar=True), flops=2.0 * F * Ho * Wo * C * 32 * 9)
 elif a.case == "headconv":      # a 256 -> 256 3x3 conv + ReLU of the prediction head over P3..P7: ONE launch of the TMA shifted-view kernel
     lv = fpn_level_sizes()
     spec = ops.ConvSpec(256, 256, 3, 1, 1)
