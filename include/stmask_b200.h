@@ -85,6 +85,7 @@ enum {
   STM_DCN_RELU = 1,          /* y = max(y, 0) in the epilogue (Featurealign.py:72)                  */
   STM_DCN_MASK_SIGMOID = 2,  /* mask holds logits; apply sigmoid while sampling (dcn_v2.DCN.forward) */
   STM_DCN_ZERO_OFFSET = 4,   /* offset == NULL: plain convolution through the same pipeline          */
+  STM_DCN_HINT_RASTER = 8,   /* tcgen05 sampling kernel: GEMM rows in raster order even where 8x8 pixel patches apply */
   /* Scheduling hints for the tcgen05 backend (results are identical; tests use them to force every CTA
    * shape through the same entry point).  Stateless: they travel with the call, there are no
    * environment variables or global knobs behind this ABI. */

@@ -17,6 +17,7 @@ STM_F32, STM_BF16 = 0, 1
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
 BACKEND_NAMES = {BACKEND_AUTO: "auto", BACKEND_SIMT: "simt", BACKEND_TCGEN05: "tcgen05"}
 DCN_RELU, DCN_MASK_SIGMOID, DCN_ZERO_OFFSET = 1, 2, 4
+DCN_HINT_RASTER = 8
 DCN_HINT_ROWS128, DCN_HINT_ROWS256, DCN_HINT_NO_PAIR = 16, 32, 64
 DCN_OUT_F32, DCN_HINT_DEEP_PIPE, DCN_HINT_TWO_CTAS = 128, 256, 512
 DCN_OUT_PLANAR = 131072

@@ -53,7 +53,7 @@ struct DcnProblemDev {
   int32_t batch, in_h, in_w, out_h, out_w;
   int32_t m_total;      // batch * out_h * out_w output pixels (GEMM rows)
   int32_t tile_begin;   // index of this problem's first M tile in the launch
-  int32_t pad_;
+  int32_t patch;        // tcgen05 kernel: GEMM rows enumerate the map in 8x8 pixel patches instead of raster order
   int64_t x_sn, x_sh, x_sw;
   int64_t y_sn, y_sh, y_sw;
   int64_t off_sn, off_sc, off_sh, off_sw;

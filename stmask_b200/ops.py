@@ -300,7 +300,7 @@ def deform_conv2d_multi(xs: Sequence[torch.Tensor], offsets: Sequence[Optional[t
         p.y = y.data_ptr()
         p.y_stride_n, p.y_stride_h, p.y_stride_w = y.stride(0), y.stride(2), y.stride(3)
     flags = (L.DCN_RELU if relu else 0) | (L.DCN_MASK_SIGMOID if mask_sigmoid else 0) | (L.DCN_ZERO_OFFSET if zero_offset else 0)
-    flags |= int(hint) & (L.DCN_HINT_ROWS128 | L.DCN_HINT_ROWS256 | L.DCN_HINT_NO_PAIR | L.DCN_HINT_DEEP_PIPE | L.DCN_HINT_TWO_CTAS | L.DCN_HINT_GATHER | L.DCN_HINT_TAP_MAJOR | L.DCN_HINT_CHUNK_MAJOR | L.DCN_HINT_NO_FUSE | (0xff << 20))
+    flags |= int(hint) & (L.DCN_HINT_ROWS128 | L.DCN_HINT_ROWS256 | L.DCN_HINT_NO_PAIR | L.DCN_HINT_DEEP_PIPE | L.DCN_HINT_TWO_CTAS | L.DCN_HINT_GATHER | L.DCN_HINT_TAP_MAJOR | L.DCN_HINT_CHUNK_MAJOR | L.DCN_HINT_NO_FUSE | L.DCN_HINT_RASTER | (0xff << 20))
     if out_f32:
         flags |= L.DCN_OUT_F32
     if out_planar:
@@ -389,7 +389,7 @@ def deform_conv2d_fcb_multi(xs: Sequence[torch.Tensor], deltas: Sequence[torch.T
         if fw.shape[0] != spec.deform_groups * 2 * spec.kernel[0] * spec.kernel[1]:
             raise ValueError("conv_offset weight does not match kernel_size / deform_groups")
     flags = (L.DCN_RELU if relu else 0) | (L.DCN_FCB_ADA if fw is not None else L.DCN_FCB_ALI)
-    flags |= int(hint) & (L.DCN_HINT_ROWS128 | L.DCN_HINT_ROWS256 | L.DCN_HINT_NO_PAIR | L.DCN_HINT_TWO_CTAS | L.DCN_HINT_TAP_MAJOR | L.DCN_HINT_CHUNK_MAJOR)
+    flags |= int(hint) & (L.DCN_HINT_ROWS128 | L.DCN_HINT_ROWS256 | L.DCN_HINT_NO_PAIR | L.DCN_HINT_TWO_CTAS | L.DCN_HINT_TAP_MAJOR | L.DCN_HINT_CHUNK_MAJOR | L.DCN_HINT_RASTER)
     conv = spec.c_struct(_dt(xs[0], "x"), odt, flags, L.BACKEND_AUTO)
     with torch.cuda.device(dev):
         rc = L.lib().stm_deform_conv2d_fcb_fwd(C.byref(conv), probs, n, w_packed.data_ptr(), None,

@@ -285,3 +285,40 @@ def test_k_order_variants_vs_oracle(cuda_device, case):
         torch.cuda.synchronize()
         err = rel_err(y.float().cpu().numpy(), want)
         assert err <= TOL, (case, hint, err)
+
+
+@pytest.mark.parametrize("case", [("fcb", (3, 5), 256, 1, [(3, 24, 40), (2, 12, 20), (2, 8, 8)]), ("dcnv2", (3, 3), 128, 2, [(5, 48, 80)]),
+                                  ("dcnv2", (3, 3), 256, 1, [(7, 24, 40)])], ids=lambda c: f"{c[0]}_C{c[2]}_s{c[3]}")
+def test_patch_row_order_is_bit_identical_to_raster_order(cuda_device, case):
+    """Maps whose sides are multiples of 8 enumerate their GEMM rows in 8x8 pixel patches (L1 / L2 locality of the gather);
+    every output pixel's arithmetic is unchanged, so the result must equal the raster-order launch (STM_DCN_HINT_RASTER) bit for
+    bit — and the oracle within tolerance."""
+    ops, L = _ops()
+    kind, (kh, kw), c, s, maps = case
+    pad = ((kh - 1) // 2, (kw - 1) // 2)
+    rng = np.random.default_rng(kh + kw + c + s)
+    spec = ops.ConvSpec(c, c, (kh, kw), s, pad)
+    w = q(rng.standard_normal((c, c, kh, kw)) / np.sqrt(c * kh * kw))
+    wp = ops.pack_weight(dev(w, BF16, cuda_device, cl=False), spec, BF16)
+    xs = [q(rng.standard_normal((b, c, h, ww))) for b, h, ww in maps]
+    xd = [dev(x, BF16, cuda_device) for x in xs]
+    outs_hw = [spec.out_hw(h, ww) for _, h, ww in maps]
+    if kind == "fcb":
+        deltas = [rng.standard_normal((b, 4, ho, wo)).astype(np.float32) for (b, _, _), (ho, wo) in zip(maps, outs_hw)]
+        w_off = (rng.standard_normal((2 * kh * kw, 4, 1, 1)) * 0.5).astype(np.float32)
+        wants = [oracle.feature_align(x, dl, w, (kh, kw), w_offset=w_off)[0] for x, dl in zip(xs, deltas)]
+        dd, wod = [dev(dl, torch.float32, cuda_device) for dl in deltas], dev(w_off, torch.float32, cuda_device, cl=False)
+        run = lambda hint: ops.deform_conv2d_fcb_multi(xd, dd, wp, spec, wod, relu=True, hint=hint)
+    else:
+        offs = [(rng.standard_normal((b, 2 * kh * kw, ho, wo)) * 2).astype(np.float32) for (b, _, _), (ho, wo) in zip(maps, outs_hw)]
+        msks = [rng.standard_normal((b, kh * kw, ho, wo)).astype(np.float32) for (b, _, _), (ho, wo) in zip(maps, outs_hw)]
+        wants = [oracle.deform_conv2d(x, o, w, None, 1.0 / (1.0 + np.exp(-m)), stride=s, padding=pad) for x, o, m in zip(xs, offs, msks)]
+        od = [dev(o, torch.float32, cuda_device, cl=False) for o in offs]            # plane-major, as the DCN module's predictor writes them
+        md = [dev(m, torch.float32, cuda_device, cl=False) for m in msks]
+        run = lambda hint: ops.deform_conv2d_multi(xd, od, md, wp, None, spec, mask_sigmoid=True, hint=hint)
+    for base in (0, L.DCN_HINT_ROWS256, L.DCN_HINT_TAP_MAJOR):
+        ya, yb = run(base), run(base | L.DCN_HINT_RASTER)
+        torch.cuda.synchronize()
+        for a, b, want in zip(ya, yb, wants):
+            assert torch.equal(a, b)
+            assert rel_err(a.float().cpu().numpy(), want) <= TOL
