@@ -103,7 +103,7 @@ enum {
   STM_DCN_FCB_ALI = 2048,       /* offsets = closed form of the box transform   (Featurealign.py:46-69)      */
   STM_DCN_HINT_TAP_MAJOR = 8192, /* K-block order (tap, chunk): sample records computed one tap ahead                        */
   STM_DCN_HINT_CHUNK_MAJOR = 16384, /* K-block order (chunk, tap) with every tap's sample records resident in shared memory
-                                   (deform_groups == 1; the default for in_c >= 256, N = 256)                 */
+                                   (the default when deform_groups == 1)                                     */
   STM_DCN_HINT_NO_FUSE = 32768, /* STM_DCN_ZERO_OFFSET only: TMA kernel without the horizontal taps fused into N (tests)      */
   STM_DCN_OUT_PLANAR = 131072,  /* y is [batch, out_c, out_h, out_w] ("NCHW"): element (b, n, h, w) at b * y_stride_n + n * (out_h * y_stride_h)
                                    + h * y_stride_h + w * y_stride_w.  tcgen05 backend only.  A DCN's offset / mask predictor writes

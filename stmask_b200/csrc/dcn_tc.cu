@@ -258,6 +258,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     // (FCB: the four box deltas (t_x, t_y, t_w, t_h) of the row instead — the same for every tap, an L1 hit after the first)
     const bool fcb_ada = FCB && (p.flags & STM_DCN_FCB_ADA) != 0;
     auto load_raw = [&](int it_, float& oy, float& ox, float& mk, float& r3) {
+      if (FCB && it_ > 0) return;              // the four box deltas are the same for every tap: loaded once, kept in registers
       oy = 0.f; ox = 0.f; mk = FCB ? 0.f : 1.f; r3 = 0.f;
       if (PLAIN || !rvalid || it_ >= n_iter) return;
       if (FCB) {
@@ -414,27 +415,12 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     GTask S[D];                             // task (kb, j) lives in S[j % D]; D tasks are in flight per thread
     float r_oy, r_ox, r_mk, r_3;
     // prologue: metadata of iteration 0, then the first D gather tasks of K block 0
-    if (CO) {
-      // every tap's record up front (dg == 1: iteration == tap).  The raw loads of three taps are in flight together
-      // (FCB: the four box deltas are the same for every tap and are loaded once).
-      if (FCB) {
-        load_raw(0, r_oy, r_ox, r_mk, r_3);
-        for (int t = 0; t < K; ++t) compute_meta(t, t, r_oy, r_ox, r_mk, r_3);
-      } else {
-        for (int t0 = 0; t0 < K; t0 += 3) {
-          float a_oy[3], a_ox[3], a_mk[3], a_3[3];
-#pragma unroll
-          for (int u = 0; u < 3; ++u) load_raw(t0 + u < K ? t0 + u : n_iter, a_oy[u], a_ox[u], a_mk[u], a_3[u]);
-#pragma unroll
-          for (int u = 0; u < 3; ++u)
-            if (t0 + u < K) compute_meta(t0 + u, t0 + u, a_oy[u], a_ox[u], a_mk[u], a_3[u]);
-        }
-      }
-    } else {
-      load_raw(0, r_oy, r_ox, r_mk, r_3);
-      compute_meta(0, 0, r_oy, r_ox, r_mk, r_3);
-      load_raw(1, r_oy, r_ox, r_mk, r_3);
-    }
+    // record of tap 0 now, the others one K block ahead of their first use: in the chunk-major order that is during the
+    // first chunk's pass over the taps (record t lives in buffer t and is reused by every later chunk), in the tap-major
+    // order once per tap (three rotating buffers)
+    load_raw(0, r_oy, r_ox, r_mk, r_3);
+    compute_meta(0, 0, r_oy, r_ox, r_mk, r_3);
+    load_raw(1, r_oy, r_ox, r_mk, r_3);
     named_barrier_sync(1, PT);
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -447,10 +433,10 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     int it = 0, cc = 0;                     // (tap, group) iteration and channel chunk of the CURRENT K block
 #pragma unroll 1
     for (int kb = 0; kb < num_kb; ++kb) {
-      if (!CO && cc == 0 && it + 1 < n_iter) {
-        // metadata one iteration ahead: buffer (it+1) % 3 was last read by the gather of iteration it-2, which
-        // every thread finished before it arrived at the previous barrier
-        compute_meta((it + 1) % META_BUFS, it + 1, r_oy, r_ox, r_mk, r_3);
+      if (cc == 0 && it + 1 < n_iter) {
+        // metadata one iteration ahead.  Tap-major: buffer (it+1) % 3 was last read by the gather of iteration it-2, which
+        // every thread finished before it arrived at the previous barrier; chunk-major: buffer it+1 is written once
+        compute_meta(CO ? it + 1 : (it + 1) % META_BUFS, it + 1, r_oy, r_ox, r_mk, r_3);
         load_raw(it + 2, r_oy, r_ox, r_mk, r_3);
         named_barrier_sync(1, PT);
       }
@@ -734,15 +720,14 @@ int make_plan(const StmDcnConv* conv, const DcnParams& p, TcPlan* out) {
   if ((conv->flags & STM_DCN_HINT_DEEP_PIPE) != 0) budget = 200 * 1024;
   // chunk-major K order: all kh*kw sample records of a row stay in shared memory (16 B each), so consecutive K blocks are
   // the neighbouring taps of ONE 64-channel chunk and re-read each other's cache lines from L1 instead of L2
-  // (B200, FCB 3x5 over 1024 frames, power-capped: 14.36 -> 14.10 ms; equal at full clocks — the kernel is bound by L1
-  // wavefronts, hits and misses alike, and what the order saves is L2 traffic, i.e. power).  Only with >= 4 chunks per tap
-  // and N = 256: at C = 128 the records' 12 KB come out of an L1 that two 3-stage CTAs have already cut to ~40 KB
-  // (0.304 -> 0.394 ms on the 48x80 layer).  STM_DCN_HINT_CHUNK_MAJOR / _TAP_MAJOR force either order.
+  // (B200, 1024 frames, with the 8x8 patch row order: FCB 3x5 13.69 -> 13.11 ms, C = 512 s2 2.08 -> 1.58 ms, C = 128 s2
+  // 4.18 -> 3.76 ms with two stages instead of three so that two CTAs still share an SM).  The default whenever
+  // deform_groups == 1 and there is more than one chunk per tap; STM_DCN_HINT_TAP_MAJOR keeps the other order.
   pl.chunk_outer = !pl.plain && p.dg == 1 && p.in_c > BLOCK_K && p.kh * p.kw > 1 && p.kh * p.kw <= 25 &&
-                   (conv->flags & STM_DCN_HINT_TAP_MAJOR) == 0 &&
-                   ((p.in_c >= 4 * BLOCK_K && pl.block_n == 256) || (conv->flags & STM_DCN_HINT_CHUNK_MAJOR) != 0);
+                   (conv->flags & STM_DCN_HINT_TAP_MAJOR) == 0;
   pl.meta_bufs = pl.chunk_outer ? p.kh * p.kw : META_BUFS;
   if (pl.chunk_outer) budget += (pl.meta_bufs - META_BUFS) * rows_per_cta * 16;
+  if (pl.two_ctas && budget > 113 * 1024) budget = 113 * 1024;          // both CTAs must still fit one SM's 227 KB
   auto total = [&](int st) {
     return pl.m_tiles == 2 ? SmemLayout<2>(pl.block_n, st, pl.pair, fcb_floats, pl.meta_bufs).total
                            : SmemLayout<1>(pl.block_n, st, pl.pair, fcb_floats, pl.meta_bufs).total;

@@ -265,7 +265,7 @@ def test_k_order_variants_vs_oracle(cuda_device, case):
     v_chunk = ops.deform_conv2d_variant([tuple(xd.shape)], spec, BF16, hint=L.DCN_HINT_CHUNK_MAJOR, fcb=kind == "fcb")
     v_tap = ops.deform_conv2d_variant([tuple(xd.shape)], spec, BF16, hint=L.DCN_HINT_TAP_MAJOR, fcb=kind == "fcb")
     assert "korder=chunk" in v_chunk and "korder=tap" in v_tap, (v_chunk, v_tap)
-    assert ("korder=chunk" in v_auto) == (cin >= 256), v_auto          # C = 128 keeps its L1 for the gather
+    assert "korder=chunk" in v_auto, v_auto
     if kind == "fcb":
         deltas = rng.standard_normal((B, 4, Ho, Wo)).astype(np.float32)
         w_off = (rng.standard_normal((2 * kh * kw, 4, 1, 1)) * 0.5).astype(np.float32)
