@@ -23,7 +23,8 @@ SOURCES = ["abi.cu", "dcn_simt.cu", "dcn_tc.cu", "conv_tma.cu", "corr_simt.cu", 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
               "-Xptxas", "-v"] + (["-DSTM_DCN_EXPERIMENTS"] if os.environ.get("STM_DCN_EXPERIMENTS") else []) + \
-             (["-DSTM_CONV_TMA_TRACE"] if os.environ.get("STM_CONV_TMA_TRACE") else [])
+             (["-DSTM_CONV_TMA_TRACE"] if os.environ.get("STM_CONV_TMA_TRACE") else []) + \
+             (["-DSTM_DCN_TRACE"] if os.environ.get("STM_DCN_TRACE") else [])
 
 
 def _nvcc() -> str:

@@ -161,6 +161,13 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
   static_assert(D >= 1 && D <= TPK && TPK % D == 0, "gather look-ahead must divide the tasks per K block");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#ifdef STM_DCN_TRACE
+  long long tr_[8];
+  tr_[0] = clock64();
+#define STM_TR(i) tr_[i] = clock64()
+#else
+#define STM_TR(i)
+#endif
   const bool CO = !PLAIN && a.chunk_outer != 0;      // (chunk, tap) K-block order, all taps' records resident (dg == 1)
   const SmemLayout<M_TILES> L(a.block_n, a.stages, PAIR, FCB ? a.p.dg * 2 * a.p.kh * a.p.kw * 4 : 0, CO ? a.p.kh * a.p.kw : META_BUFS);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -412,6 +419,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]));
     };
 
+    STM_TR(1);                              // setup done (barriers, TMEM, cluster sync)
     GTask S[D];                             // task (kb, j) lives in S[j % D]; D tasks are in flight per thread
     float r_oy, r_ox, r_mk, r_3;
     // prologue: metadata of iteration 0, then the first D gather tasks of K block 0
@@ -428,6 +436,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       read_meta(m, 0, j);
       issue(S[j], m, (uint32_t)(v * 16));
     }
+    STM_TR(2);                              // first records computed, first loads issued
     int stage = 0;
     uint32_t phase = 0;
     int it = 0, cc = 0;                     // (tap, group) iteration and channel chunk of the CURRENT K block
@@ -476,7 +485,9 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       it = nit; cc = ncc;
     }
     // =============================== EPILOGUE ===============================
+    STM_TR(3);                              // main loop done
     mbar_wait(accum_bar, 0);
+    STM_TR(4);                              // accumulators complete
     tcgen05_fence_after();
     // warp w may only touch TMEM lanes [32 (w % 4), +32).  The PW / 4 warp groups split the accumulators:
     // M_TILES == 2 -> (tile, column part); M_TILES == 1 -> column part.
@@ -506,6 +517,51 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     const bool planar = (p.flags & STM_DCN_OUT_PLANAR) != 0;       // y[b][n][ho][wo]: consecutive lanes = consecutive pixels
     const int64_t y_sc = (int64_t)pr.out_h * pr.y_sh;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * block_n);
+    // bf16 NHWC output: stage the tile in shared memory (the operand ring and the sample records are dead once the accumulators
+    // are complete) and write it out with every warp instruction covering ONE row's contiguous bytes.  A thread owns a TMEM
+    // lane = an output row, so storing straight from registers makes each 16-byte STG of a warp hit 32 different lines: 32 L1
+    // wavefronts instead of 4 per instruction, 6-11 k clk of a CTA's 58-150 k (STM_DCN_TRACE).
+    const int pitch = block_n * 2 + 16;                                  // +16 B: lanes 8 rows apart share a bank group, 4 wavefronts per STS.128
+    const bool staged = !planar && !out_f32 && ROWS * pitch + ROWS * 8 <= L.bars;
+    if (staged) {
+      uint8_t* stag = smem;
+      int64_t* s_yoff = reinterpret_cast<int64_t*>(smem + ROWS * pitch);
+      if (part == 0) s_yoff[row] = row_ok ? yoff : -1;
+      auto convert_store = [&](const uint32_t* acc, int c0) {           // 16 columns -> bias, ReLU, bf16 -> 32 bytes of the staged row
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          f[i] = __uint_as_float(acc[i]);
+          if (p.bias != nullptr) f[i] += __ldg(p.bias + n0 + c0 + i);
+          if (relu) f[i] = fmaxf(f[i], 0.f);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(stag + row * pitch + c0 * 2);
+        dst[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        dst[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+      };
+      int c0 = c_begin;
+      for (; c0 + 32 <= c_end; c0 += 32) {                             // 32 columns per TMEM round trip
+        uint32_t acc[32];
+        tmem_ld32(taddr + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        convert_store(acc, c0);
+        convert_store(acc + 16, c0 + 16);
+      }
+      for (; c0 < c_end; c0 += 16) {
+        uint32_t acc[16];
+        tmem_ld16(taddr + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        convert_store(acc, c0);
+      }
+      named_barrier_sync(1, PT);
+      const int cpr = block_n / 8;                                       // 16-byte chunks per row
+      __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(pr.y) + n0;
+      for (int i = tid; i < ROWS * cpr; i += PT) {
+        const int r = i / cpr, ch = i - r * cpr;
+        const int64_t yo = s_yoff[r];
+        if (yo >= 0) *reinterpret_cast<uint4*>(yb + yo + ch * 8) = *reinterpret_cast<const uint4*>(stag + r * pitch + ch * 16);
+      }
+    } else {
     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
       uint32_t acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
@@ -536,6 +592,13 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
         }
       }
     }
+    }
+#ifdef STM_DCN_TRACE
+    STM_TR(5);
+    if (tid == 0 && (blockIdx.x == 1000 || blockIdx.x == 1001 || blockIdx.x == 1600))
+      printf("dcn_tc cta %d: setup %lld, first records+loads %lld, main loop %lld (%d K blocks), wait accum %lld, epilogue %lld\n", (int)blockIdx.x,
+             tr_[1] - tr_[0], tr_[2] - tr_[1], tr_[3] - tr_[2], num_kb, tr_[4] - tr_[3], tr_[5] - tr_[4]);
+#endif
   } else if (warp == PW) {
     // =============================== TMA (weights) ===============================
     if (lane == 0) {
