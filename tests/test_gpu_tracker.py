@@ -153,3 +153,51 @@ def test_track_update_argument_checks(cuda_device):
         ops.track_update(trk.state, dets, torch.zeros(1, 3, 5, device=cuda_device), None, match_coeff=(0, 1, 2, 0))
     with pytest.raises(ValueError):
         ops.track_update(trk.state, dets, torch.zeros(1, 3, 4, device=cuda_device), None, match_coeff=(0, 1, 2))
+
+
+def test_clip_pipeline_glue_vs_oracle(cuda_device):
+    """stmask_b200/clip_pipeline.py: NMS -> gathers -> CandidateShift (correlation, RoIAlign, TemporalNet) -> tracker for two
+    clips over three frames.  The kernels are pinned elsewhere; here the GLUE is: the gathered detection rows must be the head's
+    rows at the NMS indices, and the tracker state must equal the numpy restatement replayed on the pipeline's own detections and shifts."""
+    from oracle import track_oracle as T
+    from stmask_b200.clip_pipeline import ClipPipeline
+    from stmask_b200.temporal_net import TemporalNet
+    g = torch.Generator(device=cuda_device).manual_seed(9)
+    rnd = lambda *s: torch.randn(*s, generator=g, device=cuda_device)
+    C, cap, K, E, P, H, W = 2, 24, 32, 16, 600, 24, 40
+    net = TemporalNet(633).to(cuda_device).to(torch.bfloat16)
+    pipe = ClipPipeline(net, C, cap, K, E, (H, W), cuda_device, top_k=12, conf_thresh=0.2, nms_thresh=0.5)
+    priors = torch.cat([torch.rand(P, 2, generator=g, device=cuda_device) * 0.8 + 0.1, torch.rand(P, 2, generator=g, device=cuda_device) * 0.2 + 0.05], 1)
+    states = [None] * C
+    for f in range(3):
+        conf = rnd(C, P, 41) * 2.0
+        preds = {"conf": conf, "loc": rnd(C, P, 4) * 0.2, "centerness": torch.rand(C, P, 1, generator=g, device=cuda_device),
+                 "mask_coeff": rnd(C, P, K), "track": torch.nn.functional.normalize(rnd(C, P, E), dim=-1), "priors": priors[None]}
+        fpn = rnd(C, 256, H, W).bfloat16().contiguous(memory_format=torch.channels_last)
+        t2s = rnd(C, 256, H, W).bfloat16().contiguous(memory_format=torch.channels_last)
+        proto = torch.relu(rnd(C, H, W, K))
+        first = torch.tensor([f == 0, f == 0])
+        out = pipe.step(preds, fpn, t2s, proto, first)
+        cnt = out["count"].cpu().numpy()
+        assert cnt.min() > 0
+        for c in range(C):
+            n = int(cnt[c])
+            idx = out["index"][c, :n].long()
+            assert torch.equal(out["coeff"][c, :n], preds["mask_coeff"][c, idx]) and torch.equal(out["track"][c, :n], preds["track"][c, idx])
+            assert torch.equal(out["centerness"][c, :n], preds["centerness"][c, idx, 0])
+            det = {"box": out["box"][c, :n].cpu().numpy(), "score": out["score"][c, :n].cpu().numpy(), "cls": out["cls"][c, :n].cpu().numpy(),
+                   "coeff": out["coeff"][c, :n].cpu().numpy(), "track": out["track"][c, :n].cpu().numpy(),
+                   "centerness": out["centerness"][c, :n].cpu().numpy()}
+            pr = proto[c].cpu().numpy()
+            det["mask"] = T.generate_mask(pr, det["coeff"], det["box"])
+            st = states[c]
+            if st is not None and f > 0:
+                m = st["box"].shape[0]
+                st = T.apply_shift(st, out["loc_shift"][c, :m].float().cpu().numpy(), out["coeff_shift"][c, :m].float().cpu().numpy(), pr)
+            states[c], want_slot, want_keep = T.track_update(st, det, f == 0, pipe.tracker.match_coeff, conf_thresh=0.2, capacity=cap)
+            m = states[c]["box"].shape[0]
+            assert int(pipe.tracker.state["n_obj"][c]) == m
+            assert np.array_equal(out["det_slot"][c, :n].cpu().numpy(), want_slot)
+            assert np.array_equal(np.nonzero(out["keep"][c].cpu().numpy())[0], np.nonzero(want_keep)[0])
+            assert np.abs(pipe.tracker.state["box"][c, :m].cpu().numpy() - states[c]["box"]).max() <= 1e-4
+            assert np.abs(pipe.tracker.state["coeff"][c, :m].cpu().numpy() - states[c]["coeff"]).max() <= 1e-4
