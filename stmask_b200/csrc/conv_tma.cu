@@ -662,7 +662,7 @@ int launch_conv_tma(const StmDcnConv* conv, const DcnParams& p, cudaStream_t str
     const CUresult r = enc(&maps.x[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(q.x), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("tma conv: cuTensorMapEncodeTiled(x) failed (%d)", (int)r); return STM_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { set_error("tma conv: cuTensorMapEncodeTiled(x) failed (%d)", (int)r); return STM_ERR_UNSUPPORTED; }
   }
   for (int i = p.n_probs; i < STM_DCN_MAX_PROBLEMS; ++i) maps.x[i] = maps.x[0];
   if (pl.args.fuse_kw) {
@@ -674,7 +674,7 @@ int launch_conv_tma(const StmDcnConv* conv, const DcnParams& p, cudaStream_t str
     const CUresult r = enc(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.w), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("tma conv: cuTensorMapEncodeTiled(w, fused) failed (%d)", (int)r); return STM_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { set_error("tma conv: cuTensorMapEncodeTiled(w, fused) failed (%d)", (int)r); return STM_ERR_UNSUPPORTED; }
   } else {
     const cuuint64_t ktot = (cuuint64_t)p.kh * p.kw * p.in_c;
     const cuuint64_t dims[2] = {ktot, (cuuint64_t)p.out_c};
@@ -684,7 +684,7 @@ int launch_conv_tma(const StmDcnConv* conv, const DcnParams& p, cudaStream_t str
     const CUresult r = enc(&maps.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.w), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("tma conv: cuTensorMapEncodeTiled(w) failed (%d)", (int)r); return STM_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { set_error("tma conv: cuTensorMapEncodeTiled(w) failed (%d)", (int)r); return STM_ERR_UNSUPPORTED; }
   }
 #define STM_CONV_GO(S_, T_, F_, SLOT_)                                                                             \
   do {                                                                                                             \

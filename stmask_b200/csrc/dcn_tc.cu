@@ -838,7 +838,11 @@ size_t dcn_tc_workspace(const StmDcnConv*, const StmDcnProblem*, int) { return 0
 
 int dcn_tc_variant(const StmDcnConv* conv, const DcnParams& p, char* buf, size_t len) {
   const char* why = "";
-  if (conv_tma_shape_supported(conv, p, &why)) return conv_tma_variant(conv, p, buf, len);
+  if (conv_tma_shape_supported(conv, p, &why)) {
+    const int rc = conv_tma_variant(conv, p, buf, len);
+    if (rc != STM_ERR_UNSUPPORTED) return rc;
+    clear_error();
+  }
   TcPlan pl;
   const int rc = make_plan(conv, p, &pl);
   if (rc != STM_OK) return rc;
@@ -860,7 +864,11 @@ int launch_dcn_tc(const StmDcnConv* conv, const DcnParams& p_in, void*, size_t, 
   {
     // regular convolutions that tile well: A operand by TMA, taps as shifted descriptor views (no gather at all)
     const char* why = "";
-    if (conv_tma_shape_supported(conv, p_in, &why)) return launch_conv_tma(conv, p_in, stream);
+    if (conv_tma_shape_supported(conv, p_in, &why)) {
+      const int rc = launch_conv_tma(conv, p_in, stream);
+      if (rc != STM_ERR_UNSUPPORTED) return rc;            // a tensor map the driver refuses (exotic strides): the gather loop below takes it
+      clear_error();
+    }
   }
   TcPlan pl;
   const int prc = make_plan(conv, p, &pl);
