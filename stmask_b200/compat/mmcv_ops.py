@@ -82,9 +82,15 @@ class DeformConv2dPack(DeformConv2d):
                                      dilation=self.dilation, bias=True)
         self.conv_offset.weight.data.zero_()
         self.conv_offset.bias.data.zero_()
+        self._predictor = ops.PlainConv()
 
     def forward(self, x):
-        return super().forward(x, self.conv_offset(x))
+        # the offset predictor is this library's own regular convolution (fp32 output: sampling positions are never rounded
+        # to bf16; plane-major so that the sampling kernel's per-tap offset loads coalesce), like dcn_v2.DCN's
+        co = self.conv_offset
+        n_off = co.weight.shape[0]
+        off = self._predictor([x], co.weight, co.bias, co.stride, co.padding, co.dilation, out_f32=True, out_planar=True)[0]
+        return super().forward(x, off[:, :n_off])
 
 
 class ModulatedDeformConv2d(nn.Module):
@@ -135,11 +141,13 @@ class ModulatedDeformConv2dPack(ModulatedDeformConv2d):
                                      dilation=self.dilation, bias=True)
         self.conv_offset.weight.data.zero_()
         self.conv_offset.bias.data.zero_()
+        self._predictor = ops.PlainConv()
 
     def forward(self, x):
-        out = self.conv_offset(x)
+        co = self.conv_offset
+        out = self._predictor([x], co.weight, co.bias, co.stride, co.padding, co.dilation, out_f32=True, out_planar=True)[0]
         n_off = 2 * self.deform_groups * self.kernel_size[0] * self.kernel_size[1]
-        return super().forward(x, out[:, :n_off], out[:, n_off:], mask_sigmoid=True)
+        return super().forward(x, out[:, :n_off], out[:, n_off:n_off + n_off // 2], mask_sigmoid=True)
 
 
 def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode="avg", aligned=True):

@@ -770,3 +770,27 @@ def test_hot_path_step_is_cuda_graph_capturable(cuda_device):
     for k, v in eager2.items():
         assert torch.equal(replayed[k], v), k
     assert not torch.equal(replayed["tf.concat"], eager["tf.concat"])
+
+
+def test_pack_modules_use_the_library_predictor(cuda_device):
+    """mmcv.ops.DeformConv2dPack / ModulatedDeformConv2dPack with NON-zero offset predictors: their conv_offset runs on this library's
+    own convolution (no cuDNN); result == the functional op fed with a torch fp32 conv2d of the same predictor."""
+    from stmask_b200 import _lib as L
+    from stmask_b200.compat.mmcv_ops import DeformConv2dPack, ModulatedDeformConv2dPack, deform_conv2d, modulated_deform_conv2d
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(4)
+    x = torch.randn(2, 32, 12, 14, device=cuda_device)
+    with torch.no_grad():
+        for cls in (DeformConv2dPack, ModulatedDeformConv2dPack):
+            m = cls(32, 48, 3, padding=1).to(cuda_device)
+            torch.nn.init.normal_(m.conv_offset.weight, std=0.05)
+            torch.nn.init.normal_(m.conv_offset.bias, std=0.3)
+            n0 = L.launch_count()
+            y = m(x)
+            assert L.launch_count() - n0 >= 2                     # predictor + sampling kernel are both this library's
+            om = torch.nn.functional.conv2d(x, m.conv_offset.weight, m.conv_offset.bias, padding=1)
+            if cls is DeformConv2dPack:
+                want = deform_conv2d(x, om, m.weight, 1, 1, 1, 1, 1)
+            else:
+                want = modulated_deform_conv2d(x, om[:, :18], torch.sigmoid(om[:, 18:]), m.weight, m.bias, 1, 1, 1, 1, 1)
+            assert rel_err(y.cpu().numpy(), want.cpu().numpy()) <= 1e-4
