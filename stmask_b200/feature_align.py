@@ -7,7 +7,8 @@ B200-specific additions:
     elementwise torch ops) or `stm_fcb_ada_offsets` (the 1x1 conv_offset);
   * the ReLU after the deformable conv (Featurealign.py:72) is fused into its epilogue;
   * `forward_levels` runs ALL FPN levels of the weight-shared head (STMask.py:91-92,
-    prediction_head_FC.py:157-167) in ONE grouped launch.
+    prediction_head_FC.py:157-167) in ONE grouped launch per conv — the output conv (Featurealign.py:73) included,
+    on this library's own convolution kernel (no cuDNN).
 """
 from __future__ import annotations
 
@@ -36,6 +37,7 @@ class FeatureAlign(nn.Module):
                                           deform_groups=deformable_groups)
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=self.kernel_size, padding=self.padding)
         self._fused = None          # None: untried, True / False: the fused-offset tcgen05 path applies / does not
+        self._out_conv = ops.PlainConv()
 
     def init_weights(self, bias_value=0):
         if self.use_pred_offset:
@@ -73,7 +75,12 @@ class FeatureAlign(nn.Module):
         return ops.deform_conv2d_multi(list(xs), offs, None, wp, None, spec, relu=True, outs=outs)
 
     def forward_levels(self, xs: Sequence[torch.Tensor], shapes: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-        return [self.conv(y) for y in self.calibrate_levels(xs, shapes)]
+        """conv(relu(conv_adaption(x, offset))) for every level (Featurealign.py:72-73): two launches for all levels, both this
+        library's (the output conv on the TMA shifted-view kernel for bf16 activations, on the CUDA-core kernel for fp32)."""
+        cal = self.calibrate_levels(xs, shapes)
+        c = self.conv
+        ys = self._out_conv(cal, c.weight, c.bias, c.stride, c.padding, c.dilation)
+        return [y[:, :c.out_channels] for y in ys]
 
     def forward(self, x, shape):
         return self.forward_levels([x], [shape])[0]
