@@ -331,7 +331,7 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       //      rows past the end) keep weight 0 and read a clamped in-map address, so the gather stays branch-free
       //      and every load is in bounds; one LDS.128 per gather task instead of 40 bytes in three loads (the shared-
       //      memory / L1 data pipe is this kernel's busiest unit: profiles/r02_dcn_fcb35_pair2.txt). ----
-      if (cg != 0) return;
+      if (!CO && cg != 0) return;             // tap-major: group 0 builds the record; chunk-major: every group builds ONE tap's
       const float h = (float)(hb + ti * p.dh) + oy;
       const float w = (float)(wb + tj * p.dw) + ox;
       const bool inside = rvalid && h > -1.f && w > -1.f && h < (float)pr.in_h && w < (float)pr.in_w;
@@ -423,12 +423,22 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     GTask S[D];                             // task (kb, j) lives in S[j % D]; D tasks are in flight per thread
     float r_oy, r_ox, r_mk, r_3;
     // prologue: metadata of iteration 0, then the first D gather tasks of K block 0
-    // record of tap 0 now, the others one K block ahead of their first use: in the chunk-major order that is during the
-    // first chunk's pass over the taps (record t lives in buffer t and is reused by every later chunk), in the tap-major
-    // order once per tap (three rotating buffers)
-    load_raw(0, r_oy, r_ox, r_mk, r_3);
-    compute_meta(0, 0, r_oy, r_ox, r_mk, r_3);
-    load_raw(1, r_oy, r_ox, r_mk, r_3);
+    // Records are built ahead of their first use.  Tap-major: thread group 0 (one thread per row) builds tap it+1 at the first
+    // chunk of tap it, three rotating buffers.  Chunk-major: record t lives in buffer t and is reused by every later chunk;
+    // the NCG = PT / ROWS thread groups each build ONE tap's records per step (group g: tap it+1+g), so a step happens every
+    // NCG K blocks of the first chunk pass — half the barriers and no idle half of the CTA (with 9 taps and 18 K blocks per
+    // tile, the C = 128 stage had a record step with half its threads waiting in every second K block).
+    constexpr int NCG = PT / ROWS;
+    if (CO) {
+      if (FCB) load_raw(0, r_oy, r_ox, r_mk, r_3);                    // the box deltas: the same for every tap
+      else load_raw(cg, r_oy, r_ox, r_mk, r_3);
+      if (cg < n_iter) compute_meta(cg, cg, r_oy, r_ox, r_mk, r_3);
+      load_raw(NCG + cg, r_oy, r_ox, r_mk, r_3);
+    } else {
+      load_raw(0, r_oy, r_ox, r_mk, r_3);
+      compute_meta(0, 0, r_oy, r_ox, r_mk, r_3);
+      load_raw(1, r_oy, r_ox, r_mk, r_3);
+    }
     named_barrier_sync(1, PT);
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -442,10 +452,18 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
     int it = 0, cc = 0;                     // (tap, group) iteration and channel chunk of the CURRENT K block
 #pragma unroll 1
     for (int kb = 0; kb < num_kb; ++kb) {
-      if (cc == 0 && it + 1 < n_iter) {
-        // metadata one iteration ahead.  Tap-major: buffer (it+1) % 3 was last read by the gather of iteration it-2, which
-        // every thread finished before it arrived at the previous barrier; chunk-major: buffer it+1 is written once
-        compute_meta(CO ? it + 1 : (it + 1) % META_BUFS, it + 1, r_oy, r_ox, r_mk, r_3);
+      if (CO) {
+        if (cc == 0 && (it % NCG) == NCG - 1 && it + 1 < n_iter) {
+          // chunk-major: records it+1 .. it+NCG, one per thread group, each buffer written once
+          const int mine = it + 1 + cg;
+          if (mine < n_iter) compute_meta(mine, mine, r_oy, r_ox, r_mk, r_3);
+          load_raw(mine + NCG, r_oy, r_ox, r_mk, r_3);
+          named_barrier_sync(1, PT);
+        }
+      } else if (cc == 0 && it + 1 < n_iter) {
+        // tap-major, one iteration ahead: buffer (it+1) % 3 was last read by the gather of iteration it-2, which every thread
+        // finished before it arrived at the previous barrier
+        compute_meta((it + 1) % META_BUFS, it + 1, r_oy, r_ox, r_mk, r_3);
         load_raw(it + 2, r_oy, r_ox, r_mk, r_3);
         named_barrier_sync(1, PT);
       }
