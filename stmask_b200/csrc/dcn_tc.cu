@@ -574,10 +574,20 @@ dcn_tc_kernel(const __grid_constant__ TcArgs a, const __grid_constant__ CUtensor
       named_barrier_sync(1, PT);
       const int cpr = block_n / 8;                                       // 16-byte chunks per row
       __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(pr.y) + n0;
-      for (int i = tid; i < ROWS * cpr; i += PT) {
-        const int r = i / cpr, ch = i - r * cpr;
-        const int64_t yo = s_yoff[r];
-        if (yo >= 0) *reinterpret_cast<uint4*>(yb + yo + ch * 8) = *reinterpret_cast<const uint4*>(stag + r * pitch + ch * 16);
+      if (cpr <= 32 && (cpr & (cpr - 1)) == 0) {
+        // a warp instruction = 32 / cpr whole rows (N = 256: one row, 512 contiguous bytes); shifts, no divisions
+        const int sh = __ffs(cpr) - 1;
+        const int rsub = lane >> sh, ch = lane & (cpr - 1), rpi = 32 >> sh;
+        for (int r = warp * rpi + rsub; r < ROWS; r += PW * rpi) {
+          const int64_t yo = s_yoff[r];
+          if (yo >= 0) *reinterpret_cast<uint4*>(yb + yo + ch * 8) = *reinterpret_cast<const uint4*>(stag + r * pitch + ch * 16);
+        }
+      } else {
+        for (int i = tid; i < ROWS * cpr; i += PT) {
+          const int r = i / cpr, ch = i - r * cpr;
+          const int64_t yo = s_yoff[r];
+          if (yo >= 0) *reinterpret_cast<uint4*>(yb + yo + ch * 8) = *reinterpret_cast<const uint4*>(stag + r * pitch + ch * 16);
+        }
       }
     } else {
     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
