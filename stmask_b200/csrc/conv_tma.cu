@@ -175,7 +175,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
         for (int c = 0; c < a.chunks; ++c) {
           const uint32_t s = astage;
           if (!((a.exp_ & 1) && ac >= (uint32_t)a.sa)) {
-          mbar_wait_relaxed(&a_empty[s], aphase ^ 1u);
+          if (a.exp_ & 32) mbar_wait_relaxed(&a_empty[s], aphase ^ 1u); else mbar_wait(&a_empty[s], aphase ^ 1u);
           uint8_t* dst = sA + s * a.a_stage_bytes;
           if (S == 1) {
             mbar_arrive_expect_tx(&a_full[s], (uint32_t)q.box_bytes);
@@ -247,7 +247,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
         }
         const uint32_t buf = tl & 1u;
         TRACE_T0;
-        mbar_wait_relaxed(&acc_empty[buf], ((tl >> 1) & 1u) ^ 1u);     // the epilogue has drained this accumulator
+        if (a.exp_ & 32) mbar_wait_relaxed(&acc_empty[buf], ((tl >> 1) & 1u) ^ 1u); else mbar_wait(&acc_empty[buf], ((tl >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
         TRACE_ADD(t_acc);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (uint32_t)a.n_mma;
@@ -256,7 +256,7 @@ conv_tma_kernel(const __grid_constant__ ConvTmaArgs a, const __grid_constant__ C
         for (int c = 0; c < a.chunks; ++c) {
           const uint32_t s = astage;
           TRACE_T0;
-          if (!((a.exp_ & 1) && ac >= (uint32_t)a.sa)) mbar_wait_relaxed(&a_full[s], aphase);
+          if (!((a.exp_ & 1) && ac >= (uint32_t)a.sa)) { if (a.exp_ & 32) mbar_wait_relaxed(&a_full[s], aphase); else mbar_wait(&a_full[s], aphase); }
           TRACE_ADD(t_a);
           tcgen05_fence_after();
           const uint64_t adesc_s = umma_desc_sw128(smem_u32(sA + s * a.a_stage_bytes));
