@@ -33,6 +33,12 @@ CASES = [
     (128, 32, (3, 3), 2, (1, 1), [(3, 25, 39)], True, False),           # stride 2 on odd sizes
     (256, 32, (3, 3), 1, (1, 1), [(3, 48, 80), (3, 11, 17), (5, 3, 5)], True, True),    # fused horizontal taps: ragged maps, several images per tile
     (64, 16, (3, 3), 1, (1, 1), [(2, 9, 130)], False, False),          # fused taps, a map wider than a tile
+    (64, 32, (1, 1), 2, (0, 0), [(3, 24, 40)], False, False),           # 1x1 stride 2 (only the even / even parity tile is read)
+    (64, 32, (3, 3), 2, (0, 0), [(3, 25, 41)], True, False),            # stride 2 without padding
+    (64, 32, (5, 5), 2, (2, 2), [(2, 24, 40)], False, True),            # 5x5 stride 2: taps two lattice steps apart
+    (64, 32, (3, 3), 1, (0, 0), [(3, 24, 40)], True, False),            # valid convolution (fused taps, no padding)
+    (64, 32, (3, 3), 1, (2, 2), [(3, 12, 20)], True, False),            # padding larger than the kernel radius
+    (128, 48, (5, 3), 2, (2, 1), [(2, 31, 47)], False, False),          # non-square stride 2 on odd sizes
 ]
 
 
