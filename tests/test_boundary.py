@@ -218,3 +218,44 @@ def test_launch_plan_is_a_pure_function_of_the_call():
     import re as _re
     stripped = _re.sub(r"#ifdef STM_DCN_EXPERIMENTS.*?#endif", "", src, flags=_re.S)
     assert "getenv" not in stripped
+
+
+def test_tma_conv_plan_properties():
+    """conv_tma.cu's launch plan over a sweep of shapes, queried without a GPU: the tile fits one 128-row accumulator (with the two
+    extra rows the fused horizontal taps read), at least 55 % of its rows are live, and which kernel runs (TMA shifted views or
+    the gather loop) never depends on how a caller chunks its batch — the two accumulate in different orders."""
+    import re
+    import torch
+    from stmask_b200 import ops
+    rx = re.compile(r"tma-conv stride=(\d) n=(\d+) fused_taps=(\d) tile=(\d+)x(\d+)x(\d+) live=([0-9.]+)")
+    seen_tma = seen_gather = 0
+    for cin, cout in ((64, 16), (128, 32), (256, 256)):
+        for (kh, kw) in ((1, 1), (3, 3), (3, 5), (5, 3)):
+            for s in (1, 2):
+                for (h, w) in ((3, 5), (6, 10), (7, 7), (12, 20), (24, 40), (23, 37), (48, 80), (96, 160), (9, 130)):
+                    spec = ops.ConvSpec(cin, cout, (kh, kw), s, (kh // 2, kw // 2))
+                    ho, wo = spec.out_hw(h, w)
+                    if ho <= 0 or wo <= 0:
+                        continue
+                    kinds = set()
+                    for b in (1, 2, 3, 8, 40):
+                        v = ops.deform_conv2d_variant([(b, cin, h, w)], spec, torch.bfloat16, zero_offset=True)
+                        m = rx.search(v)
+                        kinds.add(m is not None)
+                        if m is None:
+                            assert "plain=1" in v and "tma-conv" not in v, v
+                            continue
+                        stride, n, fused, bb, th, tw, live = int(m[1]), int(m[2]), int(m[3]), int(m[4]), int(m[5]), int(m[6]), float(m[7])
+                        assert stride == s and n == min(cout, 256) and fused == (3 if (s == 1 and (kh, kw) == (3, 3) and cout <= 32) else 0), v
+                        ex = (kw - 1) if s == 1 else (kw - 1 - kw // 2 - ((kw - 1 - kw // 2) & 1)) // 2 + (kw // 2 + 1) // 2
+                        ey = (kh - 1) if s == 1 else (kh - 1 - kh // 2 - ((kh - 1 - kh // 2) & 1)) // 2 + (kh // 2 + 1) // 2
+                        bw, bh = tw + ex, th + ey
+                        rows = (bb - 1) * bh * bw + (th - 1) * bw + tw
+                        assert rows <= 128 - (fused - 1 if fused else 0), (v, rows)
+                        assert th <= ho and tw <= wo and bb <= b and 0.0 < live <= 1.0, v
+                        if b == 40:
+                            assert live >= 0.45, v          # the 55 % rule is applied to the batch-independent tile efficiency
+                    assert len(kinds) == 1, (cin, cout, kh, kw, s, h, w)          # one kernel family whatever the batch size
+                    seen_tma += True in kinds
+                    seen_gather += False in kinds
+    assert seen_tma > 50 and seen_gather > 5
